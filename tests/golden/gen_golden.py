@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Generates the golden vectors under tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+    python tests/golden/gen_golden.py
+
+needs /root/reference (this container only): it builds oracle/_ref/ref_harness from the reference's
+own sources (oracle/Makefile) and stores, per case, the input bytes, the node parameters the
+reference derived (kernel, LUT, lut_inc, sub_sample) and every output it produced
+(IQBaseBand, FMDemod in place, AMDemod, USBDemod; FilterSink+FilterSource) as compressed .npz.
+The reference publishes no golden vectors of its own for this path.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from libsdr_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+T3 = lambda a: [(a, 103e3, 0.0), (a / 2, 99e3, 0.5), (a / 3, 300e3, 1.0)]  # noqa: E731
+
+# name, scalar, Fs, Fc, Ff, width, order, sub_sample, oFs, setcf, buffer_size, N, tone amplitude, noise
+BB_CASES = [
+    ("bb_s16_c1",        "s16", 2.4e6,  100e3,  100e3, 12.5e3, 15, 1, 48000.0, 0, 4096, 10007, 8192, 64),
+    ("bb_s16_neg_full",  "s16", 2.4e6, -100e3, -100e3, 12.5e3, 21, 1, 48000.0, 0, 8192, 30000, 32767, 0),
+    ("bb_s16_wrap",      "s16", 100e6,  100e3,  100e3, 25e3,   15, 1, 48000.0, 0, 16384, 50000, 8192, 64),
+    ("bb_s16_sdrfm",     "s16", 1e6,    100e3,  100e3, 12.5e3, 21, 1, 8000.0,  1, 16384, 40000, 8192, 64),
+    ("bb_s16_ss1",       "s16", 2.4e6,  100e3,  100e3, 12.5e3, 15, 1, 2.4e6,   0, 1024, 4099, 8192, 64),
+    ("bb_s16_inc0",      "s16", 2.4e6,  0.0,    0.0,   12.5e3, 16, 1, 48000.0, 0, 8192, 30000, 8192, 64),
+    ("bb_s16_ss7",       "s16", 2.4e6,  333e3,  250e3, 200e3,  33, 7, 0.0,     0, 1000, 9001, 12000, 64),
+    ("bb_s16_fracfc",    "s16", 2.4e6,  100e3 + 0.75, 100e3, 12.5e3, 15, 1, 48000.0, 0, 4096, 9000, 8192, 64),
+    ("bb_s8_pos",        "s8",  2.4e6,  100e3,  100e3, 12.5e3, 15, 1, 48000.0, 0, 4096, 20000, 60, 4),
+    ("bb_s8_neg",        "s8",  2.4e6, -100e3, -100e3, 12.5e3, 21, 1, 48000.0, 0, 4096, 20000, 60, 4),
+    ("bb_s8_inc0",       "s8",  2.4e6,  0.0,    0.0,   50e3,   16, 4, 0.0,     0, 2048, 10000, 60, 4),
+    ("bb_s8_wrap",       "s8",  1e6,    100e3,  100e3, 400e3,  9,  2, 0.0,     0, 2048, 10000, 127, 0),
+]
+
+# name, block, Fs, fmin, fmax, number of blocks
+OLA_CASES = [
+    ("ola_n64",  64,  20e6, 100e3, 300e3, 12),
+    ("ola_n256", 256, 20e6, -2e6, 1e6, 6),
+    ("ola_n1024_swap", 1024, 20e6, 3e6, 1e6, 3),   # fmax < fmin handled by FilterNode::addFilter
+]
+
+
+def run(args):
+    subprocess.run([HARNESS] + [str(a) for a in args], check=True)
+
+
+def main():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    with tempfile.TemporaryDirectory() as td:
+        for (name, sc, Fs, Fc, Ff, width, order, ss, oFs, setcf, bs, N, amp, noise) in BB_CASES:
+            dt = np.int16 if sc == "s16" else np.int8
+            x = synth.iq_int(N, Fs, T3(amp), noise, 0x5D120000 + len(name), dt)
+            inp = os.path.join(td, name + ".in"); x.tofile(inp)
+            pre = os.path.join(td, name)
+            run(["bb", sc, inp, bs, repr(Fs), repr(Fc), repr(Ff), repr(width), order, ss, repr(oFs), setcf, pre])
+            raw = np.fromfile(pre + ".params", dtype=np.uint8)
+            hdr = raw[:32].view(np.int64)
+            L = int(hdr[0])
+            kern = raw[32:32 + 8 * L].view(np.int32).reshape(L, 2)
+            lut = raw[32 + 8 * L:32 + 8 * L + 8 * 128].view(np.int32).reshape(128, 2)
+            np.savez_compressed(
+                os.path.join(HERE, name + ".npz"),
+                scalar=sc, Fs=Fs, Fc=Fc, Ff=Ff, width=width, order=order, sub_sample_arg=ss, oFs=oFs, setcf=setcf,
+                buffer_size=bs, x=x,
+                ref_order=L, ref_sub_sample=int(hdr[1]), ref_lut_inc=int(hdr[2]), ref_neg=int(hdr[3]),
+                ref_kernel=kern, ref_lut=lut,
+                bb=np.fromfile(pre + ".bb", dtype=dt).reshape(-1, 2),
+                counts=np.fromfile(pre + ".counts", dtype=np.uint32),
+                fm=np.fromfile(pre + ".fm", dtype=np.int16),
+                am=np.fromfile(pre + ".am", dtype=dt),
+                usb=np.fromfile(pre + ".usb", dtype=dt))
+            print("wrote", name, "ss=%d inc=%d outputs=%d" % (hdr[1], hdr[2], np.fromfile(pre + ".counts", dtype=np.uint32).sum()))
+        for (name, block, Fs, fmin, fmax, nblk) in OLA_CASES:
+            x = synth.iq_f32(block * nblk, Fs, [(0.5, 200e3, 0.0), (0.25, 1.5e6, 0.5), (0.1667, -3e6, 1.0)], 0.01, 0x5D120003)
+            inp = os.path.join(td, name + ".in"); x.tofile(inp)
+            pre = os.path.join(td, name)
+            lo, hi = (fmin, fmax) if fmin <= fmax else (fmax, fmin)   # FilterNode::addFilter swaps
+            run(["ola", inp, block, repr(Fs), repr(lo), repr(hi), pre])
+            np.savez_compressed(
+                os.path.join(HERE, name + ".npz"),
+                block=block, Fs=Fs, fmin=fmin, fmax=fmax, x=x,
+                kern=np.fromfile(pre + ".kern", dtype=np.complex64),
+                taps=np.fromfile(pre + ".taps", dtype=np.complex64),
+                out=np.fromfile(pre + ".out", dtype=np.complex64))
+            print("wrote", name)
+
+
+if __name__ == "__main__":
+    main()
