@@ -1,0 +1,158 @@
+/* sdrg.h -- C ABI of the B200-native libsdr receive-chain hot path.
+ *
+ * This is the drop-in boundary: a plain-C shared library (libsdrg.so) whose entry points are what
+ * libsdr's node classes bind to.  Each group cites the reference interface it replaces
+ * (file:line relative to the libsdr source tree).  The C++ node classes that keep libsdr's
+ * sdr::Sink<T>/Source/Buffer<T> config()/process() surface on top of these calls live in
+ * include/sdrg/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - every call returns an sdrg status (0 = ok); sdrg_last_error() gives the thread-local message.
+ *    SDRG_ERR_CONFIG maps to sdr::ConfigError, everything else to sdr::RuntimeError
+ *    (src/exception.hh:10-45).
+ *  - "_dev" entry points take DEVICE pointers and a cudaStream_t (passed as void*) and are
+ *    asynchronous; the others take HOST pointers, include the host<->device copies and return
+ *    after the result is in host memory.
+ *  - IQ samples are interleaved (re, im) pairs exactly like std::complex<T> arrays.
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with SDRG_ERR_CUDA.
+ */
+#ifndef SDRG_H
+#define SDRG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDRG_ABI_VERSION 1
+
+enum {
+  SDRG_OK = 0,
+  SDRG_ERR_CONFIG = 1,   /* -> sdr::ConfigError  */
+  SDRG_ERR_RUNTIME = 2,  /* -> sdr::RuntimeError */
+  SDRG_ERR_CUDA = 3,     /* -> sdr::RuntimeError */
+  SDRG_ERR_ARG = 4       /* -> sdr::RuntimeError */
+};
+
+/* sdr::Config::Type (src/node.hh:39-53), same numeric values. */
+enum {
+  SDRG_T_UNDEFINED = 0, SDRG_T_U8, SDRG_T_S8, SDRG_T_U16, SDRG_T_S16, SDRG_T_F32, SDRG_T_F64,
+  SDRG_T_CU8, SDRG_T_CS8, SDRG_T_CU16, SDRG_T_CS16, SDRG_T_CF32, SDRG_T_CF64
+};
+
+/* sdr::Config (src/node.hh:35-105). */
+typedef struct {
+  int    type;
+  double sample_rate;
+  size_t buffer_size;
+  size_t num_buffers;
+} sdrg_config;
+
+/* ---- runtime ---------------------------------------------------------------------------------- */
+int         sdrg_abi_version(void);
+const char *sdrg_last_error(void);
+int         sdrg_device_count(int *count);
+int         sdrg_set_device(int device);          /* device used by handles created afterwards on this thread */
+int         sdrg_device_synchronize(void);
+
+/* ---- buffer storage (replaces the malloc in RawBuffer::RawBuffer(size_t, BufferOwner*),
+ *      src/buffer.cc:23-33): pinned host memory with a same-sized device mirror.  The device-valid
+ *      range records what a GPU node last produced, so that chained GPU nodes skip the round trip
+ *      and host-only sinks get a copy back on demand. ------------------------------------------- */
+int sdrg_buffer_alloc(size_t bytes, void **host_ptr);
+int sdrg_buffer_free(void *host_ptr);
+int sdrg_buffer_is_managed(const void *host_ptr, int *managed);
+int sdrg_buffer_device_ptr(const void *host_ptr, void **dev_ptr);            /* host_ptr may point inside an allocation */
+int sdrg_buffer_mark_device_valid(const void *host_ptr, size_t bytes, void *stream); /* [host_ptr, +bytes) now lives on the device */
+int sdrg_buffer_device_valid(const void *host_ptr, size_t bytes, int *valid);
+int sdrg_buffer_invalidate_device(const void *host_ptr);                     /* host becomes authoritative again */
+int sdrg_buffer_sync_to_host(const void *host_ptr, size_t bytes);            /* no-op unless the range is device-valid and unsynced */
+
+/* ---- IQBaseBand<Scalar> (src/baseband.hh:21-297; FreqShiftBase src/freqshift.hh:13-107) -------
+ * scalar: SDRG_T_S8, SDRG_T_S16 or SDRG_T_F32.  Integer paths are bit-exact w.r.t. the reference;
+ * the float path is defined in DESIGN.md (the reference does not compile for float). */
+typedef struct sdrg_iqbb sdrg_iqbb;
+
+int sdrg_iqbb_create(int scalar, double Fc, double Ff, double width, size_t order,
+                     size_t sub_sample, double oFs, sdrg_iqbb **h);   /* ctor, baseband.hh:47-57 */
+int sdrg_iqbb_destroy(sdrg_iqbb *h);
+int sdrg_iqbb_set_center_frequency(sdrg_iqbb *h, double Fc);          /* baseband.hh:84-86  */
+int sdrg_iqbb_set_filter_frequency(sdrg_iqbb *h, double Ff);          /* baseband.hh:91-93  */
+int sdrg_iqbb_set_filter_width(sdrg_iqbb *h, double width);           /* baseband.hh:98-100 */
+int sdrg_iqbb_set_order(sdrg_iqbb *h, size_t order);                  /* baseband.hh:69-79 (history is zeroed) */
+int sdrg_iqbb_set_subsample(sdrg_iqbb *h, size_t sub_sample);         /* baseband.hh:105-107 */
+int sdrg_iqbb_set_output_sample_rate(sdrg_iqbb *h, double oFs);       /* baseband.hh:110-112 */
+/* config(): SDRG_ERR_CONFIG on a type mismatch; a config without type/rate/buffer size is ignored
+ * (returns SDRG_OK with out->type == SDRG_T_UNDEFINED).  Resets the stream state. baseband.hh:115-194 */
+int sdrg_iqbb_configure(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out);
+/* The host half of config() only (type check, sub-sampling, kernel, LUT increment, output config):
+ * touches no device, leaves the handle unconfigured for process().  Lets the design be inspected
+ * (sdrg_iqbb_get_info) on a machine without a GPU. */
+int sdrg_iqbb_design(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out);
+
+/* What config() derived; kernel/lut are written only when non-NULL (order / 128 int32 pairs, resp.
+ * float pairs for SDRG_T_F32). */
+typedef struct {
+  size_t   order;
+  size_t   sub_sample;
+  size_t   lut_inc;
+  int      negative_shift;
+  uint64_t samples_consumed;
+  uint64_t outputs_produced;
+} sdrg_iqbb_info;
+int sdrg_iqbb_get_info(const sdrg_iqbb *h, sdrg_iqbb_info *info, void *kernel, void *lut);
+
+/* process(): n_in complex samples in, the completed averages out (baseband.hh:136-223).
+ * *n_out is computed on the host (closed form) and is valid on return from both variants. */
+int sdrg_iqbb_process(sdrg_iqbb *h, const void *in, size_t n_in, void *out, size_t out_cap, size_t *n_out);
+int sdrg_iqbb_process_dev(sdrg_iqbb *h, const void *d_in, size_t n_in, void *d_out, size_t out_cap,
+                          size_t *n_out, void *stream);
+/* number of outputs the next process() of n_in samples will deliver */
+int sdrg_iqbb_outputs_for(const sdrg_iqbb *h, size_t n_in, size_t *n_out);
+
+/* ---- demodulators (src/demod.hh) -------------------------------------------------------------- */
+enum { SDRG_DEMOD_NONE = 0, SDRG_DEMOD_FM = 1, SDRG_DEMOD_AM = 2, SDRG_DEMOD_USB = 3 };
+
+/* FMDemod<iScalar,oScalar> (demod.hh:172-266, fast_atan2 src/math.hh:9-40).
+ * in_scalar S8/S16 -> int16 output; F32 -> float output (defined in DESIGN.md).
+ * Element 0 of every processed buffer is skipped exactly like the reference: with in_place != 0 it
+ * shows the bytes of the input that alias it, otherwise the output element is left untouched. */
+typedef struct sdrg_fmdemod sdrg_fmdemod;
+int sdrg_fmdemod_create(int in_scalar, sdrg_fmdemod **h);
+int sdrg_fmdemod_destroy(sdrg_fmdemod *h);
+int sdrg_fmdemod_configure(sdrg_fmdemod *h, const sdrg_config *src, sdrg_config *out);  /* demod.hh:195-226 */
+int sdrg_fmdemod_process(sdrg_fmdemod *h, const void *in, size_t n, void *out, int in_place);
+int sdrg_fmdemod_process_dev(sdrg_fmdemod *h, const void *d_in, size_t n, void *d_out, int in_place, void *stream);
+
+/* AMDemod<Scalar> (demod.hh:16-86) and USBDemod<Scalar> (demod.hh:91-166): stateless. */
+int sdrg_amdemod_configure(int scalar, const sdrg_config *src, sdrg_config *out);       /* demod.hh:35-62 */
+int sdrg_usbdemod_configure(int scalar, const sdrg_config *src, sdrg_config *out);      /* demod.hh:117-142 */
+int sdrg_amdemod_process(int scalar, const void *in, size_t n, void *out);
+int sdrg_amdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream);
+int sdrg_usbdemod_process(int scalar, const void *in, size_t n, void *out);
+int sdrg_usbdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream);
+
+/* ---- receive chain: IQBaseBand -> demod, many buffers per launch ------------------------------
+ * Equivalent to n_buffers consecutive Source::send() calls of buffer_size samples each through
+ * IQBaseBand<Scalar> -> {FM,AM,USB}Demod connected directly and in place (examples/sdr_fm.cc:48-51,
+ * src/node.cc:66-84): one fused pass on the device, intermediate base-band samples never leave
+ * HBM/L2.  Outputs are dense; counts[b] (host array, n_buffers entries, may be NULL) receives the
+ * number of outputs of buffer b.  d_bb / bb may be NULL when the base-band samples are not wanted. */
+typedef struct sdrg_rxchain sdrg_rxchain;
+int sdrg_rxchain_create(sdrg_iqbb *bb, int demod, sdrg_rxchain **h);   /* borrows bb; bb must outlive the chain */
+int sdrg_rxchain_destroy(sdrg_rxchain *h);
+int sdrg_rxchain_reset(sdrg_rxchain *h);                               /* demod state only (FM last value) */
+int sdrg_rxchain_process_dev(sdrg_rxchain *h, const void *d_in, size_t buffer_size, size_t n_buffers,
+                             void *d_bb, void *d_audio, size_t out_cap, size_t *n_out, size_t *counts,
+                             void *stream);
+int sdrg_rxchain_process(sdrg_rxchain *h, const void *in, size_t buffer_size, size_t n_buffers,
+                         void *bb, void *audio, size_t out_cap, size_t *n_out, size_t *counts);
+/* number of kernels the library has launched so far (all handles, this process) */
+int sdrg_kernel_launch_count(uint64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDRG_H */

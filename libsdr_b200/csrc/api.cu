@@ -1,0 +1,863 @@
+// api.cu -- the C ABI of libsdrg (include/sdrg.h): handles, stream state, buffer residency.
+//
+// Host-side bookkeeping only; all sample arithmetic happens in the kernels.  The carried stream
+// state of IQBaseBand (src/baseband.hh:278-296: _ring, _ring_offset, _sample_count, _last; and
+// src/freqshift.hh:97-99: _lut_count) becomes
+//   device: the last L-1 input samples (double buffered), the open window's partial sum
+//           (slot 0 of the double-buffered accumulator array)
+//   host  : r0 = position inside the open window, first = "no sample seen yet", phase0 = NCO phase
+// all of which advance in closed form with the number of samples consumed.
+#include "iqbb_kernels.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace sdrg {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_device = 0;
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- managed buffers ---------------------------------------------------------------------------
+struct ManagedBuffer {
+  char  *host = nullptr;
+  char  *dev = nullptr;
+  size_t bytes = 0;
+  int    device = 0;
+  size_t valid_lo = 0, valid_hi = 0;   // device-valid byte range (what a GPU node produced last)
+  bool   host_synced = true;           // that range has been copied back already
+  cudaEvent_t ready = nullptr;         // recorded after the producing kernels
+};
+static std::mutex g_buf_mu;
+static std::map<uintptr_t, ManagedBuffer> g_bufs;   // keyed by host base address
+
+static ManagedBuffer *find_buffer(const void *p) {   // caller holds g_buf_mu
+  if (g_bufs.empty()) return nullptr;
+  auto it = g_bufs.upper_bound((uintptr_t)p);
+  if (it == g_bufs.begin()) return nullptr;
+  --it;
+  ManagedBuffer &b = it->second;
+  if ((uintptr_t)p < (uintptr_t)b.host + (b.bytes ? b.bytes : 1)) return &b;
+  return nullptr;
+}
+
+}  // namespace sdrg
+
+using namespace sdrg;
+
+// ---- IQBaseBand handle -------------------------------------------------------------------------
+struct sdrg_iqbb {
+  IqbbDesign d;
+  int device = 0;
+  bool configured = false;
+  double nco_Fs = 0;
+  // device tables / state
+  void *d_taps = nullptr, *d_lut = nullptr;
+  void *d_hist[2] = {nullptr, nullptr};
+  void *d_acc[2] = {nullptr, nullptr};
+  size_t acc_cap = 0;
+  uint32_t acc_dirty[2] = {0, 0};
+  uint32_t taps_len = 1, hist_len = 0;
+  // stream position
+  uint32_t r0 = 0, phase0 = 0;
+  bool first = true;
+  int parity = 0;
+  uint64_t consumed = 0, produced = 0;
+  // staging for the host-pointer entry points
+  cudaStream_t stream = nullptr;
+  void *d_in = nullptr, *d_out = nullptr;
+  size_t in_cap = 0, out_cap = 0;
+};
+
+struct sdrg_fmdemod {
+  int scalar = SDRG_T_S16, device = 0;
+  void *d_last[2] = {nullptr, nullptr};
+  int parity = 0;
+  cudaStream_t stream = nullptr;
+  void *d_in = nullptr, *d_out = nullptr;
+  size_t in_cap = 0, out_cap = 0;
+};
+
+struct sdrg_rxchain {
+  sdrg_iqbb *bb = nullptr;
+  int demod = SDRG_DEMOD_NONE;
+  void *d_last[2] = {nullptr, nullptr};
+  int parity = 0;
+  void *d_in = nullptr, *d_bb = nullptr, *d_audio = nullptr;
+  size_t in_cap = 0, bb_cap = 0, audio_cap = 0;
+};
+
+namespace {
+
+size_t sample_bytes(int scalar) { return 2 * scalar_bytes(scalar); }
+size_t acc_bytes() { return 8; }   // int2 / float2
+
+size_t audio_bytes(int scalar, int demod) {
+  if (demod == SDRG_DEMOD_FM) return scalar == SDRG_T_F32 ? 4 : 2;
+  return scalar_bytes(scalar);
+}
+
+int grow(void **p, size_t *cap, size_t need) {
+  if (*cap >= need && *p) return SDRG_OK;
+  if (*p) SDRG_CUDA(cudaFree(*p));
+  *p = nullptr; *cap = 0;
+  size_t want = need < 4096 ? 4096 : need;
+  SDRG_CUDA(cudaMalloc(p, want));
+  *cap = want;
+  return SDRG_OK;
+}
+
+void free_dev(void **p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+// outputs delivered by the next n samples, and the stream position afterwards
+struct Advance { uint64_t n_out; uint32_t r0_after; uint32_t e0; };
+Advance advance(const sdrg_iqbb *h, uint64_t n) {
+  Advance a{0, h->r0, 0};
+  const uint64_t ss = h->d.sub_sample;
+  if (n == 0) return a;
+  const bool first = h->first && ss > 1;
+  const uint64_t q_last = (uint64_t)h->r0 + (n - 1) - ((first && n > 1) ? 1 : 0);
+  a.n_out = (q_last + 1) / ss;
+  a.r0_after = (uint32_t)((q_last + 1) % ss);
+  a.e0 = (uint32_t)(ss - 1 - h->r0 + (first ? 1 : 0));
+  return a;
+}
+
+int upload_design(sdrg_iqbb *h) {
+  const IqbbDesign &d = h->d;
+  const size_t L = d.order;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  free_dev(&h->d_taps); free_dev(&h->d_lut);
+  free_dev(&h->d_hist[0]); free_dev(&h->d_hist[1]);
+  if (d.scalar == SDRG_T_F32) {
+    std::vector<float> taps(2 * L), lut(256);
+    for (size_t i = 0; i < L; ++i) { taps[2 * i] = (float)d.kd_re[i]; taps[2 * i + 1] = (float)d.kd_im[i]; }
+    for (size_t j = 0; j < 128; ++j) { lut[2 * j] = (float)d.lutd_re[j]; lut[2 * j + 1] = (float)d.lutd_im[j]; }
+    h->taps_len = (uint32_t)L;
+    SDRG_CUDA(cudaMalloc(&h->d_taps, taps.size() * sizeof(float)));
+    SDRG_CUDA(cudaMemcpy(h->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SDRG_CUDA(cudaMalloc(&h->d_lut, lut.size() * sizeof(float)));
+    SDRG_CUDA(cudaMemcpy(h->d_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+  } else {
+    // leading zero taps multiply x[n-(L-1)+t] by 0: dropping them is exact and shortens the halo
+    size_t lead = 0;
+    while (lead + 1 < L && d.k_re[lead] == 0 && d.k_im[lead] == 0) ++lead;
+    const size_t Lp = L - lead;
+    std::vector<int32_t> taps(4 * Lp), lut(256);
+    for (size_t i = 0; i < Lp; ++i) {
+      const uint32_t kr = (uint32_t)d.k_re[lead + i], ki = (uint32_t)d.k_im[lead + i];
+      taps[4 * i] = (int32_t)kr; taps[4 * i + 1] = (int32_t)(ki - kr); taps[4 * i + 2] = (int32_t)(kr + ki);
+      taps[4 * i + 3] = 0;
+    }
+    for (size_t j = 0; j < 128; ++j) { lut[2 * j] = d.lut_re[j]; lut[2 * j + 1] = d.lut_im[j]; }
+    h->taps_len = (uint32_t)Lp;
+    SDRG_CUDA(cudaMalloc(&h->d_taps, taps.size() * sizeof(int32_t)));
+    SDRG_CUDA(cudaMemcpy(h->d_taps, taps.data(), taps.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    SDRG_CUDA(cudaMalloc(&h->d_lut, lut.size() * sizeof(int32_t)));
+    SDRG_CUDA(cudaMemcpy(h->d_lut, lut.data(), lut.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  h->hist_len = h->taps_len - 1;
+  const size_t hb = (h->hist_len ? h->hist_len : 1) * sample_bytes(d.scalar);
+  for (int k = 0; k < 2; ++k) {
+    SDRG_CUDA(cudaMalloc(&h->d_hist[k], hb));
+    SDRG_CUDA(cudaMemset(h->d_hist[k], 0, hb));     // ring zeroed in the ctor (baseband.hh:42-43)
+  }
+  return SDRG_OK;
+}
+
+int ensure_acc(sdrg_iqbb *h, size_t slots) {
+  if (h->acc_cap >= slots) return SDRG_OK;
+  const size_t cap = slots + slots / 2 + 64;
+  void *n0 = nullptr, *n1 = nullptr;
+  SDRG_CUDA(cudaMalloc(&n0, cap * acc_bytes()));
+  SDRG_CUDA(cudaMalloc(&n1, cap * acc_bytes()));
+  SDRG_CUDA(cudaMemset(n0, 0, cap * acc_bytes()));
+  SDRG_CUDA(cudaMemset(n1, 0, cap * acc_bytes()));
+  if (h->d_acc[0]) {   // keep the open window (slot 0 of the current parity)
+    SDRG_CUDA(cudaDeviceSynchronize());
+    SDRG_CUDA(cudaMemcpy(h->parity == 0 ? n0 : n1, h->d_acc[h->parity], acc_bytes(), cudaMemcpyDeviceToDevice));
+    cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]);
+  }
+  h->d_acc[0] = n0; h->d_acc[1] = n1;
+  h->acc_dirty[0] = h->acc_dirty[1] = 0;
+  h->acc_cap = cap;
+  return SDRG_OK;
+}
+
+void reset_stream_state(sdrg_iqbb *h) {
+  h->r0 = 0; h->phase0 = 0; h->first = true; h->consumed = 0; h->produced = 0;
+}
+
+// config()-time recomputation (baseband.hh:156-194): host part
+int design_only(sdrg_iqbb *h) {
+  IqbbDesign &d = h->d;
+  if (d.oFs > 0) {
+    d.sub_sample = size_t(d.Fs / d.oFs);
+    if (d.sub_sample < 1) d.sub_sample = 1;
+  }
+  if (d.sub_sample < 1) d.sub_sample = 1;    // the reference would divide by zero
+  if (d.sub_sample > (1u << 30)) return set_error(SDRG_ERR_CONFIG, "IQBaseBand: sub-sampling %zu too large", d.sub_sample);
+  design_kernel(d);
+  h->nco_Fs = double(d.Fs);
+  design_lut_increment(d, h->nco_Fs);
+  d.out_bs = d.source_bs / d.sub_sample;
+  if (d.source_bs % d.sub_sample) d.out_bs += 1;
+  d.out_rate = double(size_t(d.Fs) / d.sub_sample);
+  return SDRG_OK;
+}
+
+// ... and the device part: upload tables, reset the stream state
+int reconfigure(sdrg_iqbb *h) {
+  int rc = design_only(h);
+  if (rc) return rc;
+  IqbbDesign &d = h->d;
+  rc = upload_design(h);
+  if (rc) return rc;
+  rc = ensure_acc(h, d.out_bs + 2);
+  if (rc) return rc;
+  SDRG_CUDA(cudaMemset(h->d_acc[0], 0, h->acc_cap * acc_bytes()));
+  SDRG_CUDA(cudaMemset(h->d_acc[1], 0, h->acc_cap * acc_bytes()));
+  h->acc_dirty[0] = h->acc_dirty[1] = 0;
+  h->parity = 0;
+  reset_stream_state(h);
+  h->configured = true;
+  return SDRG_OK;
+}
+
+// one launch pair; n <= 2^30
+int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_audio, int demod,
+             uint64_t seg, int in_place, void *fm_last_in, void *fm_last_out, cudaStream_t st,
+             uint64_t *n_out) {
+  const Advance adv = advance(h, n);
+  *n_out = adv.n_out;
+  int rc = ensure_acc(h, adv.n_out + 2);
+  if (rc) return rc;
+  const int p = h->parity, q = p ^ 1;
+  const bool first = h->first && h->d.sub_sample > 1;
+  IqbbAccumArgs a{};
+  a.x = d_in; a.hist_in = h->d_hist[p]; a.hist_out = h->d_hist[q];
+  a.taps = h->d_taps; a.lut = h->d_lut;
+  a.acc_cur = h->d_acc[p]; a.acc_next = h->d_acc[q];
+  a.n = n; a.taps_len = h->taps_len; a.hist_len = h->hist_len;
+  a.ss = (uint32_t)h->d.sub_sample; a.r0 = h->r0; a.first = first ? 1u : 0u;
+  a.phase0 = h->phase0; a.inc = (uint32_t)(h->d.lut_inc & 0x7fffu); a.nco = h->d.lut_inc != 0 ? 1u : 0u;
+  a.neg = h->d.negative ? 1u : 0u;
+  a.zero_next = h->acc_dirty[q];
+  rc = launch_iqbb_accum(h->d.scalar, a, st);
+  if (rc) return rc;
+  IqbbFinalizeArgs f{};
+  f.acc_cur = h->d_acc[p]; f.acc_next = h->d_acc[q];
+  f.bb_out = d_bb; f.audio_out = d_audio;
+  f.fm_last_in = fm_last_in; f.fm_last_out = fm_last_out;
+  f.n_out = (uint32_t)adv.n_out; f.ss = a.ss; f.demod = (uint32_t)demod; f.e0 = adv.e0;
+  f.seg = seg; f.in_place = (uint32_t)in_place;
+  rc = launch_iqbb_finalize(h->d.scalar, f, st);
+  if (rc) return rc;
+  h->acc_dirty[p] = (uint32_t)adv.n_out + 1;   // slots this call touched
+  h->acc_dirty[q] = 1;                         // the carry
+  h->parity = q;
+  h->r0 = adv.r0_after;
+  h->first = false;
+  h->phase0 = (uint32_t)((h->phase0 + (uint64_t)n * (h->d.lut_inc & 0x7fffu)) & 0x7fffu);
+  h->consumed += n; h->produced += adv.n_out;
+  return SDRG_OK;
+}
+
+int check_handle(const sdrg_iqbb *h) {
+  if (!h) return set_error(SDRG_ERR_ARG, "IQBaseBand: null handle");
+  if (!h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: process() before config()");
+  return SDRG_OK;
+}
+
+int config_common(const char *who, int expect_type, const sdrg_config *src, bool need_rate, bool *skip) {
+  *skip = false;
+  if (!src) return set_error(SDRG_ERR_ARG, "%s: null config", who);
+  if (src->type == SDRG_T_UNDEFINED || src->buffer_size == 0 || (need_rate && src->sample_rate == 0)) {
+    *skip = true;
+    return SDRG_OK;
+  }
+  if (src->type != expect_type)
+    return set_error(SDRG_ERR_CONFIG, "Can not configure %s: Invalid type %s (%d), expected %s (%d)", who,
+                     type_name(src->type), src->type, type_name(expect_type), expect_type);
+  return SDRG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdrg_abi_version(void) { return SDRG_ABI_VERSION; }
+const char *sdrg_last_error(void) { return g_err; }
+
+int sdrg_device_count(int *count) {
+  if (!count) return set_error(SDRG_ERR_ARG, "null argument");
+  SDRG_CUDA(cudaGetDeviceCount(count));
+  return SDRG_OK;
+}
+int sdrg_set_device(int device) {
+  SDRG_CUDA(cudaSetDevice(device));
+  g_device = device;
+  return SDRG_OK;
+}
+int sdrg_device_synchronize(void) { SDRG_CUDA(cudaDeviceSynchronize()); return SDRG_OK; }
+int sdrg_kernel_launch_count(uint64_t *count) {
+  if (!count) return set_error(SDRG_ERR_ARG, "null argument");
+  *count = g_launches.load();
+  return SDRG_OK;
+}
+
+// ---- buffers -----------------------------------------------------------------------------------
+int sdrg_buffer_alloc(size_t bytes, void **host_ptr) {
+  if (!host_ptr) return set_error(SDRG_ERR_ARG, "null argument");
+  *host_ptr = nullptr;
+  ManagedBuffer b;
+  b.bytes = bytes; b.device = g_device;
+  SDRG_CUDA(cudaSetDevice(g_device));
+  SDRG_CUDA(cudaHostAlloc((void **)&b.host, bytes ? bytes : 1, cudaHostAllocPortable));
+  cudaError_t e = cudaMalloc((void **)&b.dev, bytes ? bytes : 1);
+  if (e != cudaSuccess) { cudaFreeHost(b.host); return set_error(SDRG_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  e = cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming);
+  if (e != cudaSuccess) { cudaFreeHost(b.host); cudaFree(b.dev); return set_error(SDRG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  g_bufs[(uintptr_t)b.host] = b;
+  *host_ptr = b.host;
+  return SDRG_OK;
+}
+
+int sdrg_buffer_free(void *host_ptr) {
+  if (!host_ptr) return SDRG_OK;
+  ManagedBuffer b;
+  {
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    auto it = g_bufs.find((uintptr_t)host_ptr);
+    if (it == g_bufs.end()) return set_error(SDRG_ERR_ARG, "sdrg_buffer_free: %p is not a managed buffer", host_ptr);
+    b = it->second;
+    g_bufs.erase(it);
+  }
+  cudaSetDevice(b.device);
+  cudaEventSynchronize(b.ready);
+  cudaEventDestroy(b.ready);
+  cudaFree(b.dev);
+  cudaFreeHost(b.host);
+  return SDRG_OK;
+}
+
+int sdrg_buffer_is_managed(const void *host_ptr, int *managed) {
+  if (!managed) return set_error(SDRG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  *managed = find_buffer(host_ptr) ? 1 : 0;
+  return SDRG_OK;
+}
+
+int sdrg_buffer_device_ptr(const void *host_ptr, void **dev_ptr) {
+  if (!dev_ptr) return set_error(SDRG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  ManagedBuffer *b = find_buffer(host_ptr);
+  *dev_ptr = b ? (void *)(b->dev + ((const char *)host_ptr - b->host)) : nullptr;
+  return SDRG_OK;
+}
+
+int sdrg_buffer_mark_device_valid(const void *host_ptr, size_t bytes, void *stream) {
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  ManagedBuffer *b = find_buffer(host_ptr);
+  if (!b) return set_error(SDRG_ERR_ARG, "not a managed buffer");
+  b->valid_lo = (const char *)host_ptr - b->host;
+  b->valid_hi = b->valid_lo + bytes;
+  b->host_synced = false;
+  SDRG_CUDA(cudaEventRecord(b->ready, (cudaStream_t)stream));
+  return SDRG_OK;
+}
+
+int sdrg_buffer_device_valid(const void *host_ptr, size_t bytes, int *valid) {
+  if (!valid) return set_error(SDRG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  ManagedBuffer *b = find_buffer(host_ptr);
+  *valid = 0;
+  if (b && b->valid_hi > b->valid_lo) {
+    const size_t lo = (const char *)host_ptr - b->host;
+    if (lo >= b->valid_lo && lo + bytes <= b->valid_hi) *valid = 1;
+  }
+  return SDRG_OK;
+}
+
+int sdrg_buffer_invalidate_device(const void *host_ptr) {
+  std::lock_guard<std::mutex> lk(g_buf_mu);
+  ManagedBuffer *b = find_buffer(host_ptr);
+  if (b) { b->valid_lo = b->valid_hi = 0; b->host_synced = true; }
+  return SDRG_OK;
+}
+
+int sdrg_buffer_sync_to_host(const void *host_ptr, size_t bytes) {
+  ManagedBuffer snap;
+  {
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    ManagedBuffer *b = find_buffer(host_ptr);
+    if (!b || b->host_synced || b->valid_hi <= b->valid_lo) return SDRG_OK;
+    const size_t lo = (const char *)host_ptr - b->host, hi = lo + bytes;
+    if (hi <= b->valid_lo || lo >= b->valid_hi) return SDRG_OK;     // disjoint: host copy is current
+    snap = *b;
+    b->host_synced = true;
+  }
+  SDRG_CUDA(cudaSetDevice(snap.device));
+  SDRG_CUDA(cudaEventSynchronize(snap.ready));
+  SDRG_CUDA(cudaMemcpy(snap.host + snap.valid_lo, snap.dev + snap.valid_lo, snap.valid_hi - snap.valid_lo,
+                       cudaMemcpyDeviceToHost));
+  return SDRG_OK;
+}
+
+// ---- IQBaseBand ---------------------------------------------------------------------------------
+int sdrg_iqbb_create(int scalar, double Fc, double Ff, double width, size_t order, size_t sub_sample,
+                     double oFs, sdrg_iqbb **out) {
+  if (!out) return set_error(SDRG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (scalar != SDRG_T_S8 && scalar != SDRG_T_S16 && scalar != SDRG_T_F32)
+    return set_error(SDRG_ERR_ARG, "IQBaseBand: unsupported scalar type %s (%d)", type_name(scalar), scalar);
+  if (order > kMaxOrder) return set_error(SDRG_ERR_ARG, "IQBaseBand: order %zu exceeds %zu", order, kMaxOrder);
+  sdrg_iqbb *h = new sdrg_iqbb();
+  h->device = g_device;
+  IqbbDesign &d = h->d;
+  d.scalar = scalar;
+  d.freq_shift = Fc;                       // FreqShiftBase<Scalar>(Fc, 0): the un-truncated double
+  d.Fc = int32_t(Fc); d.Ff = int32_t(Ff); d.Fs = 0; d.width = int32_t(width);
+  d.order = order < 1 ? 1 : order;
+  d.sub_sample = sub_sample;
+  d.oFs = oFs;
+  design_lut(d);
+  design_lut_increment(d, 0);
+  *out = h;
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_destroy(sdrg_iqbb *h) {
+  if (!h) return SDRG_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  else cudaDeviceSynchronize();
+  free_dev(&h->d_taps); free_dev(&h->d_lut);
+  free_dev(&h->d_hist[0]); free_dev(&h->d_hist[1]);
+  free_dev(&h->d_acc[0]); free_dev(&h->d_acc[1]);
+  free_dev(&h->d_in); free_dev(&h->d_out);
+  delete h;
+  return SDRG_OK;
+}
+
+// The setters mirror the reference: the filter setters only recompute the kernel (no state reset),
+// setCenterFrequency restarts the NCO phase (freqshift.hh:86), the rate setters reconfigure.
+static int refresh_kernel(sdrg_iqbb *h) {
+  if (!h->configured) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  const uint32_t old_hist = h->hist_len;
+  design_kernel(h->d);
+  // the history buffers depend on the stripped tap count; keep them when it is unchanged
+  std::vector<char> keep;
+  const size_t sb = sample_bytes(h->d.scalar);
+  if (old_hist) { keep.resize(old_hist * sb); SDRG_CUDA(cudaMemcpy(keep.data(), h->d_hist[h->parity], keep.size(), cudaMemcpyDeviceToHost)); }
+  int rc = upload_design(h);
+  if (rc) return rc;
+  if (h->hist_len && old_hist) {   // newest samples are at the end of the history
+    const size_t m = h->hist_len < old_hist ? h->hist_len : old_hist;
+    SDRG_CUDA(cudaMemcpy((char *)h->d_hist[h->parity] + (h->hist_len - m) * sb, keep.data() + (old_hist - m) * sb,
+                         m * sb, cudaMemcpyHostToDevice));
+  }
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_set_center_frequency(sdrg_iqbb *h, double Fc) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  h->d.Fc = int32_t(Fc);
+  h->d.freq_shift = double(h->d.Fc);       // setFrequencyShift(_Fc) receives the int32 member
+  design_lut_increment(h->d, h->nco_Fs);
+  h->phase0 = 0;                           // _lut_count = 0
+  return SDRG_OK;
+}
+int sdrg_iqbb_set_filter_frequency(sdrg_iqbb *h, double Ff) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  h->d.Ff = int32_t(Ff);
+  return refresh_kernel(h);
+}
+int sdrg_iqbb_set_filter_width(sdrg_iqbb *h, double width) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  h->d.width = int32_t(width);
+  return refresh_kernel(h);
+}
+int sdrg_iqbb_set_order(sdrg_iqbb *h, size_t order) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (order > kMaxOrder) return set_error(SDRG_ERR_ARG, "IQBaseBand: order %zu exceeds %zu", order, kMaxOrder);
+  h->d.order = order < 1 ? 1 : order;
+  if (!h->configured) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  design_kernel(h->d);
+  return upload_design(h);                 // fresh, zeroed history (the reference leaves it uninitialised)
+}
+int sdrg_iqbb_set_subsample(sdrg_iqbb *h, size_t sub_sample) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  h->d.sub_sample = sub_sample < 1 ? 1 : sub_sample;
+  if (h->d.Fs == 0 || h->d.source_bs == 0) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  return reconfigure(h);
+}
+int sdrg_iqbb_set_output_sample_rate(sdrg_iqbb *h, double oFs) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  h->d.oFs = oFs;
+  if (h->d.Fs == 0 || h->d.source_bs == 0) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  return reconfigure(h);
+}
+
+int sdrg_iqbb_configure(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
+  bool skip = false;
+  int rc = config_common("IQBaseBand", complex_type_of(h->d.scalar), src, true, &skip);
+  if (rc || skip) return rc;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  h->d.Fs = int32_t(src->sample_rate);
+  h->d.source_bs = src->buffer_size;
+  rc = reconfigure(h);
+  if (rc) return rc;
+  if (out) {
+    out->type = complex_type_of(h->d.scalar);
+    out->sample_rate = h->d.out_rate;
+    out->buffer_size = h->d.out_bs;
+    out->num_buffers = 1;
+  }
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_design(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
+  bool skip = false;
+  int rc = config_common("IQBaseBand", complex_type_of(h->d.scalar), src, true, &skip);
+  if (rc || skip) return rc;
+  h->d.Fs = int32_t(src->sample_rate);
+  h->d.source_bs = src->buffer_size;
+  h->configured = false;                    // tables are not on the device
+  rc = design_only(h);
+  if (rc) return rc;
+  if (out) {
+    out->type = complex_type_of(h->d.scalar);
+    out->sample_rate = h->d.out_rate; out->buffer_size = h->d.out_bs; out->num_buffers = 1;
+  }
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_get_info(const sdrg_iqbb *h, sdrg_iqbb_info *info, void *kernel, void *lut) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  const IqbbDesign &d = h->d;
+  if (info) {
+    info->order = d.order; info->sub_sample = d.sub_sample; info->lut_inc = d.lut_inc;
+    info->negative_shift = d.negative ? 1 : 0;
+    info->samples_consumed = h->consumed; info->outputs_produced = h->produced;
+  }
+  if (kernel) {
+    for (size_t i = 0; i < d.order; ++i) {
+      if (d.scalar == SDRG_T_F32) { ((float *)kernel)[2 * i] = (float)d.kd_re[i]; ((float *)kernel)[2 * i + 1] = (float)d.kd_im[i]; }
+      else { ((int32_t *)kernel)[2 * i] = d.k_re[i]; ((int32_t *)kernel)[2 * i + 1] = d.k_im[i]; }
+    }
+  }
+  if (lut) {
+    for (size_t j = 0; j < 128; ++j) {
+      if (d.scalar == SDRG_T_F32) { ((float *)lut)[2 * j] = (float)d.lutd_re[j]; ((float *)lut)[2 * j + 1] = (float)d.lutd_im[j]; }
+      else { ((int32_t *)lut)[2 * j] = d.lut_re[j]; ((int32_t *)lut)[2 * j + 1] = d.lut_im[j]; }
+    }
+  }
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_outputs_for(const sdrg_iqbb *h, size_t n_in, size_t *n_out) {
+  if (!h || !n_out) return set_error(SDRG_ERR_ARG, "null argument");
+  if (!h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: not configured");
+  *n_out = (size_t)advance(h, n_in).n_out;
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_process_dev(sdrg_iqbb *h, const void *d_in, size_t n_in, void *d_out, size_t out_cap,
+                          size_t *n_out, void *stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (n_out) *n_out = 0;
+  const size_t total = (size_t)advance(h, n_in).n_out;
+  if (total > out_cap) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: output buffer too small (%zu < %zu)", out_cap, total);
+  SDRG_CUDA(cudaSetDevice(h->device));
+  const size_t sb = sample_bytes(h->d.scalar);
+  size_t done = 0, produced = 0;
+  while (done < n_in) {
+    const uint32_t n = (uint32_t)((n_in - done) > (1u << 30) ? (1u << 30) : (n_in - done));
+    uint64_t got = 0;
+    rc = run_call(h, (const char *)d_in + done * sb, n, (char *)d_out + produced * sb, nullptr, SDRG_DEMOD_NONE, 0, 0,
+                  nullptr, nullptr, (cudaStream_t)stream, &got);
+    if (rc) return rc;
+    done += n; produced += got;
+  }
+  if (n_out) *n_out = produced;
+  return SDRG_OK;
+}
+
+static int own_stream(cudaStream_t *s) {
+  if (!*s) SDRG_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_process(sdrg_iqbb *h, const void *in, size_t n_in, void *out, size_t out_cap, size_t *n_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (n_out) *n_out = 0;
+  if (n_in == 0) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  if ((rc = own_stream(&h->stream))) return rc;
+  const size_t sb = sample_bytes(h->d.scalar);
+  const size_t total = (size_t)advance(h, n_in).n_out;
+  if (total > out_cap) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: output buffer too small (%zu < %zu)", out_cap, total);
+  if ((rc = grow(&h->d_in, &h->in_cap, n_in * sb))) return rc;
+  if ((rc = grow(&h->d_out, &h->out_cap, (total + 1) * sb))) return rc;
+  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n_in * sb, cudaMemcpyHostToDevice, h->stream));
+  size_t got = 0;
+  rc = sdrg_iqbb_process_dev(h, h->d_in, n_in, h->d_out, total, &got, h->stream);
+  if (rc) return rc;
+  if (got) SDRG_CUDA(cudaMemcpyAsync(out, h->d_out, got * sb, cudaMemcpyDeviceToHost, h->stream));
+  SDRG_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_out) *n_out = got;
+  return SDRG_OK;
+}
+
+// ---- FMDemod ------------------------------------------------------------------------------------
+int sdrg_fmdemod_create(int in_scalar, sdrg_fmdemod **out) {
+  if (!out) return set_error(SDRG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (in_scalar != SDRG_T_S8 && in_scalar != SDRG_T_S16 && in_scalar != SDRG_T_F32)
+    return set_error(SDRG_ERR_ARG, "FMDemod: unsupported scalar type %d", in_scalar);
+  sdrg_fmdemod *h = new sdrg_fmdemod();
+  h->scalar = in_scalar; h->device = g_device;
+  cudaError_t e = cudaSetDevice(h->device);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaMalloc(&h->d_last[k], 8);
+    if (e == cudaSuccess) e = cudaMemset(h->d_last[k], 0, 8);
+  }
+  if (e != cudaSuccess) { delete h; return set_error(SDRG_ERR_CUDA, "FMDemod: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return SDRG_OK;
+}
+int sdrg_fmdemod_destroy(sdrg_fmdemod *h) {
+  if (!h) return SDRG_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  else cudaDeviceSynchronize();
+  free_dev(&h->d_last[0]); free_dev(&h->d_last[1]); free_dev(&h->d_in); free_dev(&h->d_out);
+  delete h;
+  return SDRG_OK;
+}
+int sdrg_fmdemod_configure(sdrg_fmdemod *h, const sdrg_config *src, sdrg_config *out) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
+  bool skip = false;
+  int rc = config_common("FMDemod", complex_type_of(h->scalar), src, false, &skip);
+  if (rc || skip) return rc;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  SDRG_CUDA(cudaMemset(h->d_last[0], 0, 8));     // _last_value = 0 (demod.hh:210)
+  SDRG_CUDA(cudaMemset(h->d_last[1], 0, 8));
+  if (out) {
+    out->type = h->scalar == SDRG_T_F32 ? SDRG_T_F32 : SDRG_T_S16;
+    out->sample_rate = src->sample_rate; out->buffer_size = src->buffer_size; out->num_buffers = 1;
+  }
+  return SDRG_OK;
+}
+int sdrg_fmdemod_process_dev(sdrg_fmdemod *h, const void *d_in, size_t n, void *d_out, int in_place, void *stream) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (n == 0) return SDRG_OK;                    // demod.hh:231
+  SDRG_CUDA(cudaSetDevice(h->device));
+  if (d_in == d_out) return set_error(SDRG_ERR_ARG, "FMDemod: device input and output must not alias (pass in_place=1 for the in-place view semantics)");
+  int rc = launch_fmdemod(h->scalar, d_in, n, d_out, h->d_last[h->parity], h->d_last[h->parity ^ 1], in_place, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->parity ^= 1;
+  return SDRG_OK;
+}
+int sdrg_fmdemod_process(sdrg_fmdemod *h, const void *in, size_t n, void *out, int in_place) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (n == 0) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  int rc = own_stream(&h->stream);
+  if (rc) return rc;
+  const size_t ib = sample_bytes(h->scalar), ob = audio_bytes(h->scalar, SDRG_DEMOD_FM);
+  if ((rc = grow(&h->d_in, &h->in_cap, n * ib))) return rc;
+  if ((rc = grow(&h->d_out, &h->out_cap, n * ob))) return rc;
+  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n * ib, cudaMemcpyHostToDevice, h->stream));
+  // out of place: element 0 keeps whatever the caller's buffer holds
+  if (!in_place) SDRG_CUDA(cudaMemcpyAsync(h->d_out, out, ob, cudaMemcpyHostToDevice, h->stream));
+  rc = sdrg_fmdemod_process_dev(h, h->d_in, n, h->d_out, in_place, h->stream);
+  if (rc) return rc;
+  SDRG_CUDA(cudaMemcpyAsync(out, h->d_out, n * ob, cudaMemcpyDeviceToHost, h->stream));
+  SDRG_CUDA(cudaStreamSynchronize(h->stream));
+  return SDRG_OK;
+}
+
+// ---- AM / USB ----------------------------------------------------------------------------------
+static int envelope_configure(const char *who, int scalar, const sdrg_config *src, sdrg_config *out, bool keep_num) {
+  if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
+  if (scalar != SDRG_T_S8 && scalar != SDRG_T_S16 && scalar != SDRG_T_F32)
+    return set_error(SDRG_ERR_ARG, "%s: unsupported scalar type %d", who, scalar);
+  bool skip = false;
+  int rc = config_common(who, complex_type_of(scalar), src, false, &skip);
+  if (rc || skip) return rc;
+  if (out) {
+    out->type = scalar; out->sample_rate = src->sample_rate; out->buffer_size = src->buffer_size;
+    out->num_buffers = keep_num ? src->num_buffers : 1;
+  }
+  return SDRG_OK;
+}
+int sdrg_amdemod_configure(int scalar, const sdrg_config *src, sdrg_config *out) {
+  return envelope_configure("AMDemod", scalar, src, out, true);      // demod.hh:60-61 keeps numBuffers
+}
+int sdrg_usbdemod_configure(int scalar, const sdrg_config *src, sdrg_config *out) {
+  return envelope_configure("USBDemod", scalar, src, out, false);    // demod.hh:140-141 sets 1
+}
+int sdrg_amdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream) {
+  return launch_amdemod(scalar, d_in, n, d_out, (cudaStream_t)stream);
+}
+int sdrg_usbdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream) {
+  return launch_usbdemod(scalar, d_in, n, d_out, (cudaStream_t)stream);
+}
+static int envelope_host(bool usb, int scalar, const void *in, size_t n, void *out) {
+  if (n == 0) return SDRG_OK;
+  const size_t ib = sample_bytes(scalar), ob = scalar_bytes(scalar);
+  if (!ob) return set_error(SDRG_ERR_ARG, "demod: unsupported scalar type %d", scalar);
+  SDRG_CUDA(cudaSetDevice(g_device));
+  void *d_in = nullptr, *d_out = nullptr;
+  SDRG_CUDA(cudaMalloc(&d_in, n * ib));
+  cudaError_t e = cudaMalloc(&d_out, n * ob);
+  if (e != cudaSuccess) { cudaFree(d_in); return set_error(SDRG_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  int rc = SDRG_OK;
+  e = cudaMemcpy(d_in, in, n * ib, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) rc = usb ? launch_usbdemod(scalar, d_in, n, d_out, 0) : launch_amdemod(scalar, d_in, n, d_out, 0);
+  if (e == cudaSuccess && rc == SDRG_OK) e = cudaMemcpy(out, d_out, n * ob, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out);
+  if (e != cudaSuccess) return set_error(SDRG_ERR_CUDA, "demod: %s", cudaGetErrorString(e));
+  return rc;
+}
+int sdrg_amdemod_process(int scalar, const void *in, size_t n, void *out) { return envelope_host(false, scalar, in, n, out); }
+int sdrg_usbdemod_process(int scalar, const void *in, size_t n, void *out) { return envelope_host(true, scalar, in, n, out); }
+
+// ---- receive chain -------------------------------------------------------------------------------
+int sdrg_rxchain_create(sdrg_iqbb *bb, int demod, sdrg_rxchain **out) {
+  if (!bb || !out) return set_error(SDRG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (demod < SDRG_DEMOD_NONE || demod > SDRG_DEMOD_USB) return set_error(SDRG_ERR_ARG, "rxchain: unknown demodulator %d", demod);
+  sdrg_rxchain *h = new sdrg_rxchain();
+  h->bb = bb; h->demod = demod;
+  cudaError_t e = cudaSetDevice(bb->device);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaMalloc(&h->d_last[k], 8);
+    if (e == cudaSuccess) e = cudaMemset(h->d_last[k], 0, 8);
+  }
+  if (e != cudaSuccess) { delete h; return set_error(SDRG_ERR_CUDA, "rxchain: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return SDRG_OK;
+}
+int sdrg_rxchain_destroy(sdrg_rxchain *h) {
+  if (!h) return SDRG_OK;
+  cudaSetDevice(h->bb->device);
+  cudaDeviceSynchronize();
+  free_dev(&h->d_last[0]); free_dev(&h->d_last[1]);
+  free_dev(&h->d_in); free_dev(&h->d_bb); free_dev(&h->d_audio);
+  delete h;
+  return SDRG_OK;
+}
+int sdrg_rxchain_reset(sdrg_rxchain *h) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  SDRG_CUDA(cudaSetDevice(h->bb->device));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  SDRG_CUDA(cudaMemset(h->d_last[0], 0, 8));
+  SDRG_CUDA(cudaMemset(h->d_last[1], 0, 8));
+  return SDRG_OK;
+}
+
+int sdrg_rxchain_process_dev(sdrg_rxchain *h, const void *d_in, size_t buffer_size, size_t n_buffers,
+                             void *d_bb, void *d_audio, size_t out_cap, size_t *n_out, size_t *counts,
+                             void *stream) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  sdrg_iqbb *bb = h->bb;
+  int rc = check_handle(bb);
+  if (rc) return rc;
+  if (n_out) *n_out = 0;
+  if (buffer_size == 0 || n_buffers == 0) return SDRG_OK;
+  if (buffer_size > (1u << 30)) return set_error(SDRG_ERR_ARG, "rxchain: buffer_size %zu exceeds 2^30", buffer_size);
+  const size_t n_in = buffer_size * n_buffers;
+  const size_t total = (size_t)advance(bb, n_in).n_out;
+  if (total > out_cap) return set_error(SDRG_ERR_RUNTIME, "rxchain: output buffers too small (%zu < %zu)", out_cap, total);
+  if (counts) {    // per-buffer output counts, closed form
+    size_t prev = 0;
+    for (size_t b = 0; b < n_buffers; ++b) {
+      const size_t upto = (size_t)advance(bb, (b + 1) * buffer_size).n_out;
+      counts[b] = upto - prev; prev = upto;
+    }
+  }
+  SDRG_CUDA(cudaSetDevice(bb->device));
+  const size_t sb = sample_bytes(bb->d.scalar), ab = audio_bytes(bb->d.scalar, h->demod);
+  const size_t per_call = ((size_t)1 << 30) / buffer_size;     // whole buffers per launch
+  size_t done_b = 0, produced = 0;
+  while (done_b < n_buffers) {
+    const size_t nb = (n_buffers - done_b) < per_call ? (n_buffers - done_b) : per_call;
+    uint64_t got = 0;
+    rc = run_call(bb, (const char *)d_in + done_b * buffer_size * sb, (uint32_t)(nb * buffer_size),
+                  d_bb ? (char *)d_bb + produced * sb : nullptr,
+                  (d_audio && h->demod != SDRG_DEMOD_NONE) ? (char *)d_audio + produced * ab : nullptr,
+                  h->demod, buffer_size, 1, h->d_last[h->parity], h->d_last[h->parity ^ 1],
+                  (cudaStream_t)stream, &got);
+    if (rc) return rc;
+    if (h->demod == SDRG_DEMOD_FM) h->parity ^= 1;
+    done_b += nb; produced += got;
+  }
+  if (n_out) *n_out = produced;
+  return SDRG_OK;
+}
+
+int sdrg_rxchain_process(sdrg_rxchain *h, const void *in, size_t buffer_size, size_t n_buffers,
+                         void *bb_out, void *audio, size_t out_cap, size_t *n_out, size_t *counts) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  sdrg_iqbb *bb = h->bb;
+  int rc = check_handle(bb);
+  if (rc) return rc;
+  if (n_out) *n_out = 0;
+  if (buffer_size == 0 || n_buffers == 0) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(bb->device));
+  if ((rc = own_stream(&bb->stream))) return rc;
+  const size_t n_in = buffer_size * n_buffers;
+  const size_t total = (size_t)advance(bb, n_in).n_out;
+  if (total > out_cap) return set_error(SDRG_ERR_RUNTIME, "rxchain: output buffers too small (%zu < %zu)", out_cap, total);
+  const size_t sb = sample_bytes(bb->d.scalar), ab = audio_bytes(bb->d.scalar, h->demod);
+  if ((rc = grow(&h->d_in, &h->in_cap, n_in * sb))) return rc;
+  if ((rc = grow(&h->d_bb, &h->bb_cap, (total + 1) * sb))) return rc;
+  if ((rc = grow(&h->d_audio, &h->audio_cap, (total + 1) * (ab ? ab : 1)))) return rc;
+  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n_in * sb, cudaMemcpyHostToDevice, bb->stream));
+  size_t got = 0;
+  rc = sdrg_rxchain_process_dev(h, h->d_in, buffer_size, n_buffers, h->d_bb, h->d_audio, total, &got, counts, bb->stream);
+  if (rc) return rc;
+  if (got && bb_out) SDRG_CUDA(cudaMemcpyAsync(bb_out, h->d_bb, got * sb, cudaMemcpyDeviceToHost, bb->stream));
+  if (got && audio && h->demod != SDRG_DEMOD_NONE)
+    SDRG_CUDA(cudaMemcpyAsync(audio, h->d_audio, got * ab, cudaMemcpyDeviceToHost, bb->stream));
+  SDRG_CUDA(cudaStreamSynchronize(bb->stream));
+  if (n_out) *n_out = got;
+  return SDRG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// common.cuh -- shared declarations of the libsdrg implementation (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/sdrg.h"
+
+namespace sdrg {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);          // stores the thread-local message, returns code
+void count_launch(unsigned n = 1);                      // kernel launch counter (sdrg_kernel_launch_count)
+
+#define SDRG_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::sdrg::set_error(SDRG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+  } while (0)
+
+#define SDRG_CHECK_LAUNCH(name)                                                                 \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return ::sdrg::set_error(SDRG_ERR_CUDA, "launch of %s failed: %s", name,                  \
+                               cudaGetErrorString(_e));                                         \
+    ::sdrg::count_launch();                                                                     \
+  } while (0)
+
+// ---- scalar helpers ---------------------------------------------------------------------------
+static inline size_t scalar_bytes(int scalar) {
+  switch (scalar) {
+    case SDRG_T_S8: return 1; case SDRG_T_S16: return 2; case SDRG_T_F32: return 4; default: return 0;
+  }
+}
+static inline int complex_type_of(int scalar) {
+  switch (scalar) {
+    case SDRG_T_S8: return SDRG_T_CS8; case SDRG_T_S16: return SDRG_T_CS16;
+    case SDRG_T_F32: return SDRG_T_CF32; default: return SDRG_T_UNDEFINED;
+  }
+}
+const char *type_name(int type);   // sdr::typeName(), src/node.hh:141-158
+
+// ---- IQBaseBand design (host, double precision; design.cc) ------------------------------------
+struct IqbbDesign {
+  // constructor / setter state (reference members, src/baseband.hh:264-296, src/freqshift.hh:90-104)
+  int      scalar = SDRG_T_S16;
+  double   freq_shift = 0;           // FreqShiftBase::_freq_shift
+  int32_t  Fc = 0, Ff = 0, Fs = 0, width = 0;
+  size_t   order = 1, sub_sample = 1;
+  double   oFs = 0;
+  size_t   source_bs = 0;
+  // derived
+  size_t   lut_inc = 0;
+  bool     negative = false;
+  size_t   out_bs = 0;
+  double   out_rate = 0;
+  int32_t  k_re[1024], k_im[1024];   // 2^14-scaled integer kernel
+  double   kd_re[1024], kd_im[1024]; // alpha/norm (float variant)
+  int32_t  lut_re[128], lut_im[128]; // integer LUT (2^shift scaled, truncated; int16-wrapped for S8)
+  double   lutd_re[128], lutd_im[128];
+};
+static const size_t kMaxOrder = 1024;
+void design_lut(IqbbDesign &d);
+void design_kernel(IqbbDesign &d);
+void design_lut_increment(IqbbDesign &d, double nco_Fs);
+
+}  // namespace sdrg

@@ -1,0 +1,121 @@
+// demod_kernels.cu -- stand-alone FMDemod / AMDemod / USBDemod kernels (one buffer per launch).
+// Reference semantics: src/demod.hh:65-81 (AM), 156-161 (USB), 242-254 (FM), src/math.hh:12-40.
+// These are HBM-streaming elementwise kernels: 4 (2, 8) bytes in and 2 (1, 4) bytes out per
+// sample, one sample per thread-iteration, grid-stride, coalesced.
+#include "iqbb_kernels.cuh"
+#include "demod_math.cuh"
+
+namespace sdrg {
+namespace {
+
+template <int SCALAR> struct In;
+template <> struct In<SDRG_T_S16> {
+  typedef short2 T; typedef short Fm; typedef short Au; typedef int Last;
+  static __device__ __forceinline__ int2 get(const T v) { return make_int2(v.x, v.y); }
+  static __device__ __forceinline__ Last phi(int2 v) { return fm_phi_int(v.x, v.y); }
+  static __device__ __forceinline__ Fm fm(Last l, Last p) { return (short)(l - p); }
+  static __device__ __forceinline__ Fm first(int2 v) { return (short)v.x; }
+  static __device__ __forceinline__ Au am(int2 v) { return (short)am_int(v.x, v.y); }
+  static __device__ __forceinline__ Au usb(int2 v) { return (short)usb_int(v.x, v.y); }
+};
+template <> struct In<SDRG_T_S8> {
+  typedef char2 T; typedef short Fm; typedef signed char Au; typedef int Last;
+  static __device__ __forceinline__ int2 get(const T v) { return make_int2(v.x, v.y); }
+  static __device__ __forceinline__ Last phi(int2 v) { return fm_phi_int(v.x, v.y); }
+  static __device__ __forceinline__ Fm fm(Last l, Last p) { return (short)(l - p); }
+  static __device__ __forceinline__ Fm first(int2 v) {
+    return (short)(((uint32_t)(uint8_t)v.x) | (((uint32_t)(uint8_t)v.y) << 8));
+  }
+  static __device__ __forceinline__ Au am(int2 v) { return (signed char)am_int(v.x, v.y); }
+  static __device__ __forceinline__ Au usb(int2 v) { return (signed char)usb_int(v.x, v.y); }
+};
+template <> struct In<SDRG_T_F32> {
+  typedef float2 T; typedef float Fm; typedef float Au; typedef double Last;
+  static __device__ __forceinline__ float2 get(const T v) { return v; }
+  static __device__ __forceinline__ Last phi(float2 v) { return fm_phi_f64((double)v.x, (double)v.y); }
+  static __device__ __forceinline__ Fm fm(Last l, Last p) { return (float)(l - p); }
+  static __device__ __forceinline__ Fm first(float2 v) { return v.x; }
+  static __device__ __forceinline__ Au am(float2 v) { return sqrtf(v.x * v.x + v.y * v.y); }
+  static __device__ __forceinline__ Au usb(float2 v) { return (v.x + v.y) / 2; }
+};
+
+// out[i] = phi(in[i-1]) - phi(in[i]) for i >= 2, out[1] = last - phi(in[1]); element 0 skipped.
+template <int SCALAR>
+__global__ void __launch_bounds__(256) fmdemod_kernel(const typename In<SCALAR>::T *in, size_t n,
+                                                       typename In<SCALAR>::Fm *out,
+                                                       const typename In<SCALAR>::Last *last_in,
+                                                       typename In<SCALAR>::Last *last_out, int in_place) {
+  typedef In<SCALAR> I;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const auto v = I::get(in[i]);
+    if (i == 0) {
+      if (in_place) out[0] = I::first(v);
+      if (n == 1) *last_out = *last_in;
+      continue;
+    }
+    const typename I::Last p = I::phi(v);
+    const typename I::Last l = (i == 1) ? *last_in : I::phi(I::get(in[i - 1]));
+    out[i] = I::fm(l, p);
+    if (i == n - 1) *last_out = p;
+  }
+}
+
+template <int SCALAR, bool USB>
+__global__ void __launch_bounds__(256) envelope_kernel(const typename In<SCALAR>::T *in, size_t n,
+                                                        typename In<SCALAR>::Au *out) {
+  typedef In<SCALAR> I;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const auto v = I::get(in[i]);
+    out[i] = USB ? I::usb(v) : I::am(v);
+  }
+}
+
+unsigned grid_for(size_t n) {
+  size_t g = (n + 255) / 256;
+  const size_t cap = 148 * 16;          // 16 resident CTAs of 256 threads per SM, 148 SMs
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int launch_fmdemod(int scalar, const void *in, size_t n, void *out, const void *last_in, void *last_out,
+                   int in_place, cudaStream_t st) {
+  if (n == 0) return SDRG_OK;
+  const unsigned g = grid_for(n);
+  switch (scalar) {
+    case SDRG_T_S16:
+      fmdemod_kernel<SDRG_T_S16><<<g, 256, 0, st>>>((const short2 *)in, n, (short *)out, (const int *)last_in, (int *)last_out, in_place); break;
+    case SDRG_T_S8:
+      fmdemod_kernel<SDRG_T_S8><<<g, 256, 0, st>>>((const char2 *)in, n, (short *)out, (const int *)last_in, (int *)last_out, in_place); break;
+    case SDRG_T_F32:
+      fmdemod_kernel<SDRG_T_F32><<<g, 256, 0, st>>>((const float2 *)in, n, (float *)out, (const double *)last_in, (double *)last_out, in_place); break;
+    default: return set_error(SDRG_ERR_ARG, "FMDemod: unsupported scalar %d", scalar);
+  }
+  SDRG_CHECK_LAUNCH("fmdemod_kernel");
+  return SDRG_OK;
+}
+
+template <bool USB>
+static int launch_envelope(int scalar, const void *in, size_t n, void *out, cudaStream_t st) {
+  if (n == 0) return SDRG_OK;
+  const unsigned g = grid_for(n);
+  switch (scalar) {
+    case SDRG_T_S16: envelope_kernel<SDRG_T_S16, USB><<<g, 256, 0, st>>>((const short2 *)in, n, (short *)out); break;
+    case SDRG_T_S8: envelope_kernel<SDRG_T_S8, USB><<<g, 256, 0, st>>>((const char2 *)in, n, (signed char *)out); break;
+    case SDRG_T_F32: envelope_kernel<SDRG_T_F32, USB><<<g, 256, 0, st>>>((const float2 *)in, n, (float *)out); break;
+    default: return set_error(SDRG_ERR_ARG, "demod: unsupported scalar %d", scalar);
+  }
+  SDRG_CHECK_LAUNCH(USB ? "usbdemod_kernel" : "amdemod_kernel");
+  return SDRG_OK;
+}
+
+int launch_amdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t st) {
+  return launch_envelope<false>(scalar, in, n, out, st);
+}
+int launch_usbdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t st) {
+  return launch_envelope<true>(scalar, in, n, out, st);
+}
+
+}  // namespace sdrg

@@ -1,0 +1,432 @@
+// iqbb_kernels.cu -- IQBaseBand<Scalar> on the device: the direct (unfolded) kernels.
+//
+// Reference semantics: src/baseband.hh:198-236 (FIR -> NCO mix -> boxcar decimation, in this
+// order, with a truncating shift after the FIR and after the mix) and src/freqshift.hh:58-74.
+// Closed-form restatement used here: with n the sample index since
+// config(), y[n] = (sum_t k[t] x[n-(L-1)+t]) >> 14, z[n] = (lut[idx(n)] y[n]) >> shift with
+// idx(n) = ((n*inc) mod 32768) >> 8, and output m = trunc_div(wrap32(S_m*ss), wrap32(ss*ss)),
+// S_m = sum of z over window W_0=[0..ss], W_m=[m*ss+1..(m+1)*ss].  All integer sums are taken in
+// Z/2^32, which is associative, so the parallel evaluation order below is bit-exact.
+//
+// Kernel 1 (iqbb_accum_*): one CTA per tile of 2048 input samples.
+//   stage tile + (L-1) halo in shared memory -> register-blocked FIR (8 outputs per thread, a
+//   rotating 8-sample register window, taps broadcast from shared memory; the integer complex
+//   multiply uses the 3-multiplication Gauss form, exact in Z/2^32) -> NCO -> z to shared memory
+//   -> per-window partial sums (one warp or one thread per window) -> RED.ADD into the per-call
+//   window accumulators in global memory (L2-resident, 8 B per OUTPUT sample).
+// Kernel 2 (iqbb_finalize_*): one thread per completed window: division / narrowing, optional
+//   fused FM/AM/USB demodulation, carries the open window into the next call.
+#include "iqbb_kernels.cuh"
+#include "demod_math.cuh"
+
+namespace sdrg {
+
+namespace {
+
+constexpr int kT = kIqbbThreads;
+constexpr int kR = kIqbbPerThread;
+constexpr int kTile = kIqbbTile;
+constexpr int kZRow = kT + 2;              // row pitch of the transposed z staging (bank spread)
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }   // 4-byte elements, 8 per thread
+__device__ __forceinline__ int pad64(int i) { return i + (i >> 3); }   // 8-byte elements, 8 per thread
+
+__device__ __forceinline__ void unpack16(uint32_t v, int &re, int &im) {
+  re = (int)(short)(v & 0xffffu);
+  im = ((int)v) >> 16;
+}
+
+// window bookkeeping (call-relative sample index i): q(i) = r0 + i - (first && i>0); slot = q/ss
+struct WindowGrid {
+  uint32_t ss, r0, first;
+  __device__ __forceinline__ uint64_t q(uint32_t i) const { return (uint64_t)r0 + i - ((first && i > 0) ? 1u : 0u); }
+  __device__ __forceinline__ uint32_t slot(uint32_t i) const { return (uint32_t)(q(i) / ss); }
+  __device__ __forceinline__ int64_t begin(uint32_t s) const {
+    return s == 0 ? 0 : (int64_t)((uint64_t)s * ss) - (int64_t)r0 + (int64_t)first;
+  }
+  __device__ __forceinline__ int64_t end(uint32_t s) const {
+    return (int64_t)((uint64_t)(s + 1) * ss) - (int64_t)r0 + (int64_t)first;
+  }
+};
+
+// ---- shared prologue: zero the next call's accumulators, roll the history ----------------------
+template <typename Sample, typename Acc>
+__device__ __forceinline__ void prologue(const IqbbAccumArgs &a) {
+  Acc *nxt = (Acc *)a.acc_next;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < a.zero_next; k += gridDim.x * blockDim.x) {
+    Acc zero; zero.x = 0; zero.y = 0;
+    nxt[k] = zero;
+  }
+  if (blockIdx.x == 0) {
+    const Sample *x = (const Sample *)a.x;
+    const Sample *hi = (const Sample *)a.hist_in;
+    Sample *ho = (Sample *)a.hist_out;
+    const int64_t H = a.hist_len, n = a.n;
+    for (int64_t k = threadIdx.x; k < H; k += blockDim.x) {
+      const int64_t i = n - H + k;                       // call-relative source index
+      ho[k] = (i >= 0) ? x[i] : hi[H + i];
+    }
+  }
+}
+
+// ---- integer kernel ------------------------------------------------------------------------------
+// taps: int4 {kr, ki-kr, kr+ki, 0} per tap (Gauss: t1=kr(xr+xi), t2=(ki-kr)xr, t3=(kr+ki)xi;
+// re=t1-t3, im=t1+t2 -- ring identities, hence exact mod 2^32).
+template <bool IS_S8>
+__global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = (int)a.hist_len, Lp = (int)a.taps_len;
+  const int n_xs = kTile + H + 8;
+  int4 *tp = (int4 *)smem_raw;                                   // Lp
+  int2 *lut = (int2 *)(tp + Lp);                                 // 128
+  int2 *zs = lut + 128;                                          // kR * kZRow
+  uint32_t *xs = (uint32_t *)(zs + kR * kZRow);                  // pad32(n_xs)+1
+
+  if (IS_S8) prologue<char2, int2>(a); else prologue<short2, int2>(a);
+
+  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+  // stage taps / LUT / samples
+  for (int k = tid; k < Lp; k += kT) tp[k] = ((const int4 *)a.taps)[k];
+  if (tid < 128) lut[tid] = ((const int2 *)a.lut)[tid];
+  for (int k = tid; k < n_xs; k += kT) {
+    const int64_t i = tile_base - H + k;
+    uint32_t v = 0;
+    if (IS_S8) {
+      char2 s = make_char2(0, 0);
+      if (i < 0) s = ((const char2 *)a.hist_in)[H + i];
+      else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
+      v = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
+    } else {
+      if (i < 0) v = ((const uint32_t *)a.hist_in)[H + i];
+      else if (i < (int64_t)a.n) v = ((const uint32_t *)a.x)[i];
+    }
+    xs[pad32(k)] = v;
+  }
+  __syncthreads();
+
+  // FIR: outputs ob..ob+7 of the tile; window sample c lives at xs[ob + c]
+  const int ob = tid * kR;
+  uint32_t A1[kR], A2[kR], A3[kR];
+  int wr[kR], wi[kR], ws[kR];
+#pragma unroll
+  for (int c = 0; c < kR; ++c) {
+    A1[c] = A2[c] = A3[c] = 0u;
+    unpack16(xs[pad32(ob + c)], wr[c], wi[c]);
+    ws[c] = wr[c] + wi[c];
+  }
+  for (int t0 = 0; t0 < Lp; t0 += kR) {
+#pragma unroll
+    for (int u = 0; u < kR; ++u) {
+      const int t = t0 + u;
+      if (t < Lp) {
+        const int4 c = tp[t];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          const int s = (r + u) & (kR - 1);
+          A1[r] += (uint32_t)c.x * (uint32_t)ws[s];
+          A2[r] += (uint32_t)c.y * (uint32_t)wr[s];
+          A3[r] += (uint32_t)c.z * (uint32_t)wi[s];
+        }
+        unpack16(xs[pad32(ob + t + kR)], wr[u], wi[u]);   // slot u is dead now: next window sample
+        ws[u] = wr[u] + wi[u];
+      }
+    }
+  }
+
+  // >>14, NCO, stage z (transposed: row r, column tid)
+  const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    int yr = ((int)(A1[r] - A3[r])) >> 14;
+    int yi = ((int)(A1[r] + A2[r])) >> 14;
+    if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }   // narrowed to complex<int16_t> on the call
+    if (a.nco) {
+      const uint32_t ph = (a.phase0 + (i0 + r) * a.inc) & 0x7fffu;
+      uint32_t idx = ph >> 8;
+      if (a.neg) idx = 127u - idx;
+      const int2 l = lut[idx];
+      const uint32_t pr = (uint32_t)l.x * (uint32_t)yr - (uint32_t)l.y * (uint32_t)yi;
+      const uint32_t pi = (uint32_t)l.x * (uint32_t)yi + (uint32_t)l.y * (uint32_t)yr;
+      if (IS_S8) {   // product narrowed to int16, shifted by 8, narrowed again (freqshift.hh:67)
+        yr = (int)(short)(((int)(short)pr) >> 8);
+        yi = (int)(short)(((int)(short)pi) >> 8);
+      } else {
+        yr = ((int)pr) >> 16;
+        yi = ((int)pi) >> 16;
+      }
+    }
+    zs[r * kZRow + tid] = make_int2(yr, yi);
+  }
+  __syncthreads();
+
+  // per-window partial sums of this tile
+  const uint32_t tile_lo = (uint32_t)tile_base;
+  const uint32_t tile_hi = (uint32_t)min((int64_t)a.n, tile_base + kTile);
+  if (tile_hi <= tile_lo) return;
+  WindowGrid g{a.ss, a.r0, a.first};
+  const uint32_t slot_lo = g.slot(tile_lo), slot_hi = g.slot(tile_hi - 1);
+  int *acc = (int *)a.acc_cur;
+  if (a.ss >= 16) {
+    for (uint32_t s = slot_lo + warp; s <= slot_hi; s += kT / 32) {
+      const int lo = (int)(max(g.begin(s), (int64_t)tile_lo) - tile_base);
+      const int hi = (int)(min(g.end(s), (int64_t)tile_hi) - tile_base);
+      uint32_t sr = 0, si = 0;
+      for (int o = lo + lane; o < hi; o += 32) {
+        const int2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
+        sr += (uint32_t)z.x; si += (uint32_t)z.y;
+      }
+      sr = __reduce_add_sync(kFull, sr);
+      si = __reduce_add_sync(kFull, si);
+      if (lane == 0) { atomicAdd(acc + 2 * (size_t)s, (int)sr); atomicAdd(acc + 2 * (size_t)s + 1, (int)si); }
+    }
+  } else {
+    for (uint32_t s = slot_lo + tid; s <= slot_hi; s += kT) {
+      const int lo = (int)(max(g.begin(s), (int64_t)tile_lo) - tile_base);
+      const int hi = (int)(min(g.end(s), (int64_t)tile_hi) - tile_base);
+      uint32_t sr = 0, si = 0;
+      for (int o = lo; o < hi; ++o) {
+        const int2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
+        sr += (uint32_t)z.x; si += (uint32_t)z.y;
+      }
+      atomicAdd(acc + 2 * (size_t)s, (int)sr); atomicAdd(acc + 2 * (size_t)s + 1, (int)si);
+    }
+  }
+}
+
+// ---- float kernel (direct form; the folded fast path lives in iqbb_fold_kernels.cu) ---------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+
+__global__ void __launch_bounds__(kT) iqbb_accum_f32_kernel(const IqbbAccumArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = (int)a.hist_len, Lp = (int)a.taps_len;
+  const int n_xs = kTile + H + 8;
+  float2 *tp = (float2 *)smem_raw;                               // Lp (rounded up to even count)
+  float2 *lut = tp + ((Lp + 1) & ~1);                            // 128
+  float2 *zs = lut + 128;                                        // kR * kZRow
+  float2 *xs = zs + kR * kZRow;                                  // pad64(n_xs)+1
+
+  prologue<float2, float2>(a);
+
+  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+  for (int k = tid; k < Lp; k += kT) tp[k] = ((const float2 *)a.taps)[k];
+  if (tid < 128) lut[tid] = ((const float2 *)a.lut)[tid];
+  for (int k = tid; k < n_xs; k += kT) {
+    const int64_t i = tile_base - H + k;
+    float2 v = make_float2(0.f, 0.f);
+    if (i < 0) v = ((const float2 *)a.hist_in)[H + i];
+    else if (i < (int64_t)a.n) v = ((const float2 *)a.x)[i];
+    xs[pad64(k)] = v;
+  }
+  __syncthreads();
+
+  const int ob = tid * kR;
+  float yr[kR], yi[kR];
+  float2 w[kR];
+#pragma unroll
+  for (int c = 0; c < kR; ++c) { yr[c] = 0.f; yi[c] = 0.f; w[c] = xs[pad64(ob + c)]; }
+  for (int t0 = 0; t0 < Lp; t0 += kR) {
+#pragma unroll
+    for (int u = 0; u < kR; ++u) {
+      const int t = t0 + u;
+      if (t < Lp) {
+        const float2 c = tp[t];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          const int s = (r + u) & (kR - 1);
+          yr[r] = fmaf(c.x, w[s].x, yr[r]); yr[r] = fmaf(-c.y, w[s].y, yr[r]);
+          yi[r] = fmaf(c.x, w[s].y, yi[r]); yi[r] = fmaf(c.y, w[s].x, yi[r]);
+        }
+        w[u] = xs[pad64(ob + t + kR)];
+      }
+    }
+  }
+  const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    float zr = yr[r], zi = yi[r];
+    if (a.nco) {
+      const uint32_t ph = (a.phase0 + (i0 + r) * a.inc) & 0x7fffu;
+      uint32_t idx = ph >> 8;
+      if (a.neg) idx = 127u - idx;
+      const float2 l = lut[idx];
+      zr = l.x * yr[r] - l.y * yi[r];
+      zi = l.x * yi[r] + l.y * yr[r];
+    }
+    zs[r * kZRow + tid] = make_float2(zr, zi);
+  }
+  __syncthreads();
+
+  const uint32_t tile_lo = (uint32_t)tile_base;
+  const uint32_t tile_hi = (uint32_t)min((int64_t)a.n, tile_base + kTile);
+  if (tile_hi <= tile_lo) return;
+  WindowGrid g{a.ss, a.r0, a.first};
+  const uint32_t slot_lo = g.slot(tile_lo), slot_hi = g.slot(tile_hi - 1);
+  float *acc = (float *)a.acc_cur;
+  if (a.ss >= 16) {
+    for (uint32_t s = slot_lo + warp; s <= slot_hi; s += kT / 32) {
+      const int lo = (int)(max(g.begin(s), (int64_t)tile_lo) - tile_base);
+      const int hi = (int)(min(g.end(s), (int64_t)tile_hi) - tile_base);
+      float sr = 0.f, si = 0.f;
+      for (int o = lo + lane; o < hi; o += 32) {
+        const float2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
+        sr += z.x; si += z.y;
+      }
+      sr = warp_sum(sr); si = warp_sum(si);
+      if (lane == 0) { atomicAdd(acc + 2 * (size_t)s, sr); atomicAdd(acc + 2 * (size_t)s + 1, si); }
+    }
+  } else {
+    for (uint32_t s = slot_lo + tid; s <= slot_hi; s += kT) {
+      const int lo = (int)(max(g.begin(s), (int64_t)tile_lo) - tile_base);
+      const int hi = (int)(min(g.end(s), (int64_t)tile_hi) - tile_base);
+      float sr = 0.f, si = 0.f;
+      for (int o = lo; o < hi; ++o) {
+        const float2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
+        sr += z.x; si += z.y;
+      }
+      atomicAdd(acc + 2 * (size_t)s, sr); atomicAdd(acc + 2 * (size_t)s + 1, si);
+    }
+  }
+}
+
+// ---- finalize + demodulate ----------------------------------------------------------------------
+template <int SCALAR> struct Fin;
+template <> struct Fin<SDRG_T_S16> {
+  typedef int2 Acc; typedef short2 Bb; typedef short Fm; typedef short Au; typedef int Last;
+  static __device__ __forceinline__ int2 value(const Acc s, uint32_t ss) {
+    if (ss == 1) return make_int2((int)(short)s.x, (int)(short)s.y);
+    return make_int2((int)(short)cdiv_component(s.x, (int)ss), (int)(short)cdiv_component(s.y, (int)ss));
+  }
+  static __device__ __forceinline__ Bb store(int2 v) { return make_short2((short)v.x, (short)v.y); }
+  static __device__ __forceinline__ Last phi(int2 v) { return fm_phi_int(v.x, v.y); }
+  static __device__ __forceinline__ Fm fm(Last last, Last p) { return (short)(last - p); }
+  static __device__ __forceinline__ Fm fm_first(int2 v) { return (short)v.x; }
+  static __device__ __forceinline__ Au am(int2 v) { return (short)am_int(v.x, v.y); }
+  static __device__ __forceinline__ Au usb(int2 v) { return (short)usb_int(v.x, v.y); }
+};
+template <> struct Fin<SDRG_T_S8> {
+  typedef int2 Acc; typedef char2 Bb; typedef short Fm; typedef signed char Au; typedef int Last;
+  static __device__ __forceinline__ int2 value(const Acc s, uint32_t ss) {
+    if (ss == 1) return make_int2((int)(signed char)s.x, (int)(signed char)s.y);
+    return make_int2((int)(signed char)cdiv_component(s.x, (int)ss), (int)(signed char)cdiv_component(s.y, (int)ss));
+  }
+  static __device__ __forceinline__ Bb store(int2 v) { return make_char2((signed char)v.x, (signed char)v.y); }
+  static __device__ __forceinline__ Last phi(int2 v) { return fm_phi_int(v.x, v.y); }
+  static __device__ __forceinline__ Fm fm(Last last, Last p) { return (short)(last - p); }
+  static __device__ __forceinline__ Fm fm_first(int2 v) {   // int16 view of the two int8 bytes
+    return (short)(((uint32_t)(uint8_t)v.x) | (((uint32_t)(uint8_t)v.y) << 8));
+  }
+  static __device__ __forceinline__ Au am(int2 v) { return (signed char)am_int(v.x, v.y); }
+  static __device__ __forceinline__ Au usb(int2 v) { return (signed char)usb_int(v.x, v.y); }
+};
+template <> struct Fin<SDRG_T_F32> {
+  typedef float2 Acc; typedef float2 Bb; typedef float Fm; typedef float Au; typedef double Last;
+  static __device__ __forceinline__ float2 value(const Acc s, uint32_t ss) {
+    if (ss == 1) return s;
+    const float d = (float)ss;
+    return make_float2(s.x / d, s.y / d);
+  }
+  static __device__ __forceinline__ Bb store(float2 v) { return v; }
+  static __device__ __forceinline__ Last phi(float2 v) { return fm_phi_f64((double)v.x, (double)v.y); }
+  static __device__ __forceinline__ Fm fm(Last last, Last p) { return (float)(last - p); }
+  static __device__ __forceinline__ Fm fm_first(float2 v) { return v.x; }
+  static __device__ __forceinline__ Au am(float2 v) { return sqrtf(v.x * v.x + v.y * v.y); }
+  static __device__ __forceinline__ Au usb(float2 v) { return (v.x + v.y) / 2; }
+};
+
+// is output j the first element of its segment (= of the buffer it is delivered with)?
+__device__ __forceinline__ bool seg_first(uint32_t j, const IqbbFinalizeArgs &a) {
+  if (j == 0) return true;
+  if (a.seg == 0) return false;
+  const uint64_t e = (uint64_t)a.e0 + (uint64_t)j * a.ss;      // call-relative completing sample
+  return (e / a.seg) != ((e - a.ss) / a.seg);
+}
+
+template <int SCALAR>
+__global__ void __launch_bounds__(256) iqbb_finalize_kernel(const IqbbFinalizeArgs a) {
+  typedef Fin<SCALAR> F;
+  const typename F::Acc *acc = (const typename F::Acc *)a.acc_cur;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) ((typename F::Acc *)a.acc_next)[0] = acc[a.n_out];       // carry the open window
+  if (a.demod == SDRG_DEMOD_FM && j == 0) {                             // carried FM angle
+    typename F::Last last = *(const typename F::Last *)a.fm_last_in;
+    for (int64_t k = (int64_t)a.n_out - 1; k >= 0; --k) {
+      if (!seg_first((uint32_t)k, a)) { last = F::phi(F::value(acc[k], a.ss)); break; }
+    }
+    *(typename F::Last *)a.fm_last_out = last;
+  }
+  if (j >= a.n_out) return;
+  const auto v = F::value(acc[j], a.ss);
+  if (a.bb_out) ((typename F::Bb *)a.bb_out)[j] = F::store(v);
+  if (!a.audio_out) return;
+  if (a.demod == SDRG_DEMOD_AM) { ((typename F::Au *)a.audio_out)[j] = F::am(v); return; }
+  if (a.demod == SDRG_DEMOD_USB) { ((typename F::Au *)a.audio_out)[j] = F::usb(v); return; }
+  if (a.demod != SDRG_DEMOD_FM) return;
+  typename F::Fm *out = (typename F::Fm *)a.audio_out;
+  if (seg_first(j, a)) {              // element 0 of a buffer is skipped (demod.hh:245)
+    if (a.in_place) out[j] = F::fm_first(v);
+    return;
+  }
+  int64_t k = (int64_t)j - 1;
+  while (k >= 0 && seg_first((uint32_t)k, a)) --k;
+  const typename F::Last last = (k >= 0) ? F::phi(F::value(acc[k], a.ss))
+                                         : *(const typename F::Last *)a.fm_last_in;
+  out[j] = F::fm(last, F::phi(v));
+}
+
+size_t accum_smem_int(uint32_t Lp, uint32_t H) {
+  return sizeof(int4) * Lp + sizeof(int2) * 128 + sizeof(int2) * kR * kZRow +
+         sizeof(uint32_t) * ((kTile + H + 8) + ((kTile + H + 8) >> 5) + 1);
+}
+size_t accum_smem_f32(uint32_t Lp, uint32_t H) {
+  return sizeof(float2) * ((Lp + 1) & ~1u) + sizeof(float2) * 128 + sizeof(float2) * kR * kZRow +
+         sizeof(float2) * ((kTile + H + 8) + ((kTile + H + 8) >> 3) + 1);
+}
+
+}  // namespace
+
+int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st) {
+  if (a.n == 0) return SDRG_OK;
+  const unsigned grid = (unsigned)((a.n + kTile - 1) / kTile);
+  if (scalar == SDRG_T_F32) {
+    const size_t smem = accum_smem_f32(a.taps_len, a.hist_len);
+    if (smem > 48 * 1024)
+      SDRG_CUDA(cudaFuncSetAttribute(iqbb_accum_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    iqbb_accum_f32_kernel<<<grid, kT, smem, st>>>(a);
+    SDRG_CHECK_LAUNCH("iqbb_accum_f32_kernel");
+  } else {
+    const size_t smem = accum_smem_int(a.taps_len, a.hist_len);
+    if (scalar == SDRG_T_S8) {
+      if (smem > 48 * 1024)
+        SDRG_CUDA(cudaFuncSetAttribute(iqbb_accum_int_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      iqbb_accum_int_kernel<true><<<grid, kT, smem, st>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        SDRG_CUDA(cudaFuncSetAttribute(iqbb_accum_int_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      iqbb_accum_int_kernel<false><<<grid, kT, smem, st>>>(a);
+    }
+    SDRG_CHECK_LAUNCH("iqbb_accum_int_kernel");
+  }
+  return SDRG_OK;
+}
+
+int launch_iqbb_finalize(int scalar, const IqbbFinalizeArgs &a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.n_out + 255) / 256);
+  const unsigned g = grid ? grid : 1;     // the carry must be moved even when nothing completed
+  switch (scalar) {
+    case SDRG_T_S16: iqbb_finalize_kernel<SDRG_T_S16><<<g, 256, 0, st>>>(a); break;
+    case SDRG_T_S8: iqbb_finalize_kernel<SDRG_T_S8><<<g, 256, 0, st>>>(a); break;
+    case SDRG_T_F32: iqbb_finalize_kernel<SDRG_T_F32><<<g, 256, 0, st>>>(a); break;
+    default: return set_error(SDRG_ERR_ARG, "finalize: unsupported scalar %d", scalar);
+  }
+  SDRG_CHECK_LAUNCH("iqbb_finalize_kernel");
+  return SDRG_OK;
+}
+
+}  // namespace sdrg

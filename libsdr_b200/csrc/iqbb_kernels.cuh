@@ -1,0 +1,59 @@
+// iqbb_kernels.cuh -- launch parameter blocks and launch wrappers of the IQBaseBand kernels.
+#pragma once
+#include "common.cuh"
+
+namespace sdrg {
+
+constexpr int kIqbbThreads = 256;      // threads per CTA of the accumulate kernels
+constexpr int kIqbbPerThread = 8;      // consecutive FIR outputs per thread (register blocking)
+constexpr int kIqbbTile = kIqbbThreads * kIqbbPerThread;   // input samples per CTA
+
+// One process() call of the direct (unfolded) kernels.  All indices are relative to the first
+// sample of the call; the host carries the global position (closed form).
+struct IqbbAccumArgs {
+  const void *x;          // n input samples (char2 / short2 / float2), device
+  const void *hist_in;    // the previous `hist_len` samples (same type), device
+  void       *hist_out;   // receives the last `hist_len` samples of [hist_in | x]
+  const void *taps;       // int: 3 x Lp int32 (Gauss form, see iqbb_kernels.cu); float: Lp float2
+  const void *lut;        // 128 x int2 or 128 x float2
+  void       *acc_cur;    // window accumulators of this call (int2 / float2), slot 0 = open window
+  void       *acc_next;   // accumulators of the next call: zeroed here (first `zero_next` entries)
+  uint32_t    n;
+  uint32_t    taps_len;   // Lp: number of (stripped) taps
+  uint32_t    hist_len;   // Lp - 1
+  uint32_t    ss;
+  uint32_t    r0;         // position of sample 0 inside its window
+  uint32_t    first;      // 1 if sample 0 is the very first sample since config() (window 0 has ss+1)
+  uint32_t    phase0;     // NCO phase (15 bit) at sample 0
+  uint32_t    inc;        // NCO increment mod 32768
+  uint32_t    nco;        // 0: lut_inc == 0, the mixer is bypassed entirely (freqshift.hh:61)
+  uint32_t    neg;        // negative frequency shift: idx = 127 - idx
+  uint32_t    zero_next;
+};
+
+// finalize (+ optional demodulation) of the completed windows of one call
+struct IqbbFinalizeArgs {
+  const void *acc_cur;    // n_out completed slots followed by the open one
+  void       *acc_next;   // slot 0 receives the carry
+  void       *bb_out;     // complex Scalar[n_out] or null
+  void       *audio_out;  // demod output or null
+  const void *fm_last_in; // carried FM angle (int16 as int32 / double), device scalar
+  void       *fm_last_out;
+  uint32_t    n_out;
+  uint32_t    ss;
+  uint32_t    demod;      // SDRG_DEMOD_*
+  uint32_t    e0;         // call-relative index of the sample that completes slot 0
+  uint64_t    seg;        // buffer_size (segment length in input samples); 0 = one segment
+  uint32_t    in_place;   // FM: what element 0 of every segment shows
+};
+
+int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st);
+int launch_iqbb_finalize(int scalar, const IqbbFinalizeArgs &a, cudaStream_t st);
+
+// stand-alone demodulators (demod_kernels.cu)
+int launch_fmdemod(int scalar, const void *in, size_t n, void *out, const void *last_in, void *last_out,
+                   int in_place, cudaStream_t st);
+int launch_amdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t st);
+int launch_usbdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t st);
+
+}  // namespace sdrg

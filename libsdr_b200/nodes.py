@@ -1,0 +1,264 @@
+"""Host-side mirror (Python) of the libsdr node interface for the hot path.
+
+Same names, constructor arguments, config()/process() meaning and error behaviour as
+  IQBaseBand<Scalar>      src/baseband.hh:21-297
+  FMDemod<iScalar,oScalar> src/demod.hh:172-266
+  AMDemod / USBDemod      src/demod.hh:16-166
+on top of the C ABI (include/sdrg.h).  Arrays are numpy (host entry points) or torch CUDA tensors
+(device entry points, asynchronous on the current torch stream).  The C++ mirror of the same
+interface (sdr::Sink<T>/Source/Buffer<T>) is include/sdrg/*.hh.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (Config, ConfigError, T_S8, T_S16, T_F32, T_CS8, T_CS16, T_CF32,  # noqa: F401
+                   DEMOD_NONE, DEMOD_FM, DEMOD_AM, DEMOD_USB)
+
+_SCALARS = {"s8": T_S8, "s16": T_S16, "f32": T_F32, np.int8: T_S8, np.int16: T_S16, np.float32: T_F32,
+            T_S8: T_S8, T_S16: T_S16, T_F32: T_F32}
+_NP = {T_S8: np.int8, T_S16: np.int16, T_F32: np.float32}
+_CTYPE = {T_S8: T_CS8, T_S16: T_CS16, T_F32: T_CF32}
+
+
+def scalar_id(s):
+    if isinstance(s, np.dtype):
+        s = s.type
+    return _SCALARS[s]
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def fm_out_dtype(scalar):
+    return np.float32 if scalar == T_F32 else np.int16
+
+
+class IQBaseBand:
+    """IQBaseBand<Scalar>(Fc, Ff, width, order, sub_sample, oFs=0)  (src/baseband.hh:47-57).
+    The 5-argument reference constructor (Ff = Fc, baseband.hh:35) is `IQBaseBand(scalar, Fc, None, ...)`."""
+
+    def __init__(self, scalar, Fc, Ff, width, order, sub_sample, oFs=0.0):
+        self.scalar = scalar_id(scalar)
+        self.dtype = _NP[self.scalar]
+        self._h = C.c_void_p()
+        if Ff is None:
+            Ff = Fc
+        _lib.call("sdrg_iqbb_create", self.scalar, float(Fc), float(Ff), float(width), int(order),
+                  int(sub_sample), float(oFs), C.byref(self._h))
+        self.out_config = Config()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_iqbb_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # setters (baseband.hh:69-112)
+    def setCenterFrequency(self, Fc): _lib.call("sdrg_iqbb_set_center_frequency", self._h, float(Fc))
+    def setFilterFrequency(self, Ff): _lib.call("sdrg_iqbb_set_filter_frequency", self._h, float(Ff))
+    def setFilterWidth(self, w): _lib.call("sdrg_iqbb_set_filter_width", self._h, float(w))
+    def setOrder(self, o): _lib.call("sdrg_iqbb_set_order", self._h, int(o))
+    def setSubsample(self, ss): _lib.call("sdrg_iqbb_set_subsample", self._h, int(ss))
+    def setOutputSampleRate(self, fs): _lib.call("sdrg_iqbb_set_output_sample_rate", self._h, float(fs))
+
+    def config(self, src_cfg=None, *, type=None, sample_rate=0.0, buffer_size=0, num_buffers=1):
+        """config(const Config&) (baseband.hh:115-132). Raises ConfigError on a type mismatch."""
+        if src_cfg is None:
+            src_cfg = Config(self._ctype() if type is None else type, sample_rate, buffer_size, num_buffers)
+        out = Config()
+        _lib.call("sdrg_iqbb_configure", self._h, C.byref(src_cfg), C.byref(out))
+        self.out_config = out
+        return out
+
+    def design_only(self, src_cfg=None, *, type=None, sample_rate=0.0, buffer_size=0, num_buffers=1):
+        """Host half of config() (no device needed); the node stays unconfigured for process()."""
+        if src_cfg is None:
+            src_cfg = Config(self._ctype() if type is None else type, sample_rate, buffer_size, num_buffers)
+        out = Config()
+        _lib.call("sdrg_iqbb_design", self._h, C.byref(src_cfg), C.byref(out))
+        self.out_config = out
+        return out
+
+    def _ctype(self):
+        return _CTYPE[self.scalar]
+
+    def info(self):
+        inf = _lib.IqbbInfo()
+        _lib.call("sdrg_iqbb_get_info", self._h, C.byref(inf), None, None)
+        return inf
+
+    def design(self):
+        """(kernel, lut) exactly as the node uses them: int32 pairs, or float32 pairs for f32."""
+        inf = self.info()
+        dt = np.float32 if self.scalar == T_F32 else np.int32
+        k = np.zeros((inf.order, 2), dtype=dt); lut = np.zeros((128, 2), dtype=dt)
+        _lib.call("sdrg_iqbb_get_info", self._h, C.byref(inf), _np_ptr(k), _np_ptr(lut))
+        return k, lut
+
+    def outputs_for(self, n_in):
+        n = C.c_size_t(0)
+        _lib.call("sdrg_iqbb_outputs_for", self._h, int(n_in), C.byref(n))
+        return n.value
+
+    def process(self, x):
+        """process(buffer): returns the outputs this buffer completes (baseband.hh:136-223)."""
+        if _is_torch(x):
+            import torch
+            n_in = x.shape[0]
+            n_out = self.outputs_for(n_in)
+            out = torch.empty((max(n_out, 1), 2), dtype=x.dtype, device=x.device)
+            got = C.c_size_t(0)
+            _lib.call("sdrg_iqbb_process_dev", self._h, C.c_void_p(x.data_ptr()), n_in,
+                      C.c_void_p(out.data_ptr()), n_out, C.byref(got), _stream_ptr())
+            return out[:got.value]
+        x = np.ascontiguousarray(x, dtype=self.dtype).reshape(-1, 2)
+        n_out = self.outputs_for(x.shape[0])
+        out = np.zeros((n_out, 2), dtype=self.dtype)
+        got = C.c_size_t(0)
+        _lib.call("sdrg_iqbb_process", self._h, _np_ptr(x), x.shape[0], _np_ptr(out), n_out, C.byref(got))
+        return out[:got.value]
+
+
+class FMDemod:
+    """FMDemod<iScalar, oScalar> (src/demod.hh:172-266); int input -> int16, float -> float."""
+
+    def __init__(self, scalar):
+        self.scalar = scalar_id(scalar)
+        self._h = C.c_void_p()
+        _lib.call("sdrg_fmdemod_create", self.scalar, C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_fmdemod_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def config(self, src_cfg):
+        out = Config()
+        _lib.call("sdrg_fmdemod_configure", self._h, C.byref(src_cfg), C.byref(out))
+        return out
+
+    def process(self, x, in_place=True, out=None):
+        """Element 0 is skipped like the reference: in_place -> the aliased input bytes, else `out[0]`
+        (or 0 when no `out` array is passed) is left untouched."""
+        if _is_torch(x):
+            import torch
+            n = x.shape[0]
+            odt = torch.float32 if self.scalar == T_F32 else torch.int16
+            if out is None:
+                out = torch.zeros(max(n, 1), dtype=odt, device=x.device)
+            _lib.call("sdrg_fmdemod_process_dev", self._h, C.c_void_p(x.data_ptr()), n,
+                      C.c_void_p(out.data_ptr()), int(in_place), _stream_ptr())
+            return out[:n]
+        x = np.ascontiguousarray(x, dtype=_NP[self.scalar]).reshape(-1, 2)
+        n = x.shape[0]
+        if out is None:
+            out = np.zeros(n, dtype=fm_out_dtype(self.scalar))
+        _lib.call("sdrg_fmdemod_process", self._h, _np_ptr(x), n, _np_ptr(out), int(in_place))
+        return out
+
+
+class _Envelope:
+    _name = ""
+
+    def __init__(self, scalar):
+        self.scalar = scalar_id(scalar)
+
+    def config(self, src_cfg):
+        out = Config()
+        _lib.call("sdrg_%s_configure" % self._name, self.scalar, C.byref(src_cfg), C.byref(out))
+        return out
+
+    def process(self, x):
+        if _is_torch(x):
+            import torch
+            n = x.shape[0]
+            out = torch.empty(max(n, 1), dtype=x.dtype, device=x.device)
+            _lib.call("sdrg_%s_process_dev" % self._name, self.scalar, C.c_void_p(x.data_ptr()), n,
+                      C.c_void_p(out.data_ptr()), _stream_ptr())
+            return out[:n]
+        x = np.ascontiguousarray(x, dtype=_NP[self.scalar]).reshape(-1, 2)
+        out = np.zeros(x.shape[0], dtype=_NP[self.scalar])
+        _lib.call("sdrg_%s_process" % self._name, self.scalar, _np_ptr(x), x.shape[0], _np_ptr(out))
+        return out
+
+
+class AMDemod(_Envelope):
+    """AMDemod<Scalar> (src/demod.hh:16-86)."""
+    _name = "amdemod"
+
+
+class USBDemod(_Envelope):
+    """USBDemod<Scalar> (src/demod.hh:91-166)."""
+    _name = "usbdemod"
+
+
+class RxChain:
+    """IQBaseBand -> demod over many buffers per launch (sdrg_rxchain_*): the equivalent of
+    n_buffers Source::send() calls through directly connected, in-place nodes."""
+
+    def __init__(self, baseband, demod):
+        self.bb = baseband
+        self.demod = demod
+        self._h = C.c_void_p()
+        _lib.call("sdrg_rxchain_create", baseband._h, int(demod), C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_rxchain_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def reset(self):
+        _lib.call("sdrg_rxchain_reset", self._h)
+
+    def audio_dtype(self):
+        if self.demod == DEMOD_FM:
+            return fm_out_dtype(self.bb.scalar)
+        return self.bb.dtype
+
+    def process(self, x, buffer_size, bb_out=None, audio_out=None):
+        """x: (n_buffers*buffer_size, 2). Returns (bb, audio, counts)."""
+        n_total = x.shape[0]
+        assert n_total % buffer_size == 0
+        nb = n_total // buffer_size
+        n_out = self.bb.outputs_for(n_total)
+        counts = (C.c_size_t * nb)()
+        got = C.c_size_t(0)
+        if _is_torch(x):
+            import torch
+            adt = {np.int16: torch.int16, np.int8: torch.int8, np.float32: torch.float32}[self.audio_dtype()]
+            if bb_out is None:
+                bb_out = torch.empty((max(n_out, 1), 2), dtype=x.dtype, device=x.device)
+            if audio_out is None:
+                audio_out = torch.zeros(max(n_out, 1), dtype=adt, device=x.device)
+            _lib.call("sdrg_rxchain_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb,
+                      C.c_void_p(bb_out.data_ptr()), C.c_void_p(audio_out.data_ptr()), n_out,
+                      C.byref(got), counts, _stream_ptr())
+            return bb_out[:got.value], audio_out[:got.value], np.array(counts[:], dtype=np.int64)
+        x = np.ascontiguousarray(x, dtype=self.bb.dtype).reshape(-1, 2)
+        if bb_out is None:
+            bb_out = np.zeros((n_out, 2), dtype=self.bb.dtype)
+        if audio_out is None:
+            audio_out = np.zeros(n_out, dtype=self.audio_dtype())
+        _lib.call("sdrg_rxchain_process", self._h, _np_ptr(x), buffer_size, nb, _np_ptr(bb_out),
+                  _np_ptr(audio_out), n_out, C.byref(got), counts)
+        return bb_out[:got.value], audio_out[:got.value], np.array(counts[:], dtype=np.int64)
