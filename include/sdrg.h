@@ -152,6 +152,13 @@ int sdrg_rxchain_process(sdrg_rxchain *h, const void *in, size_t buffer_size, si
 /* number of kernels the library has launched so far (all handles, this process) */
 int sdrg_kernel_launch_count(uint64_t *count);
 
+/* ---- measurement hooks: CUDA events recorded on the launching stream around each kernel of the
+ *      given kind while enabled; sdrg_profile_read() waits for them, returns the summed device
+ *      time and the launch count, and clears them. ---------------------------------------------- */
+enum { SDRG_KERNEL_IQBB_ACCUM = 1, SDRG_KERNEL_IQBB_FINALIZE = 2, SDRG_KERNEL_OLA = 3, SDRG_KERNEL_BANK = 4 };
+int sdrg_profile_enable(int on);
+int sdrg_profile_read(int kind, double *total_ms, uint64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

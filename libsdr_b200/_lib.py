@@ -94,6 +94,8 @@ SIGNATURES = {
     "sdrg_rxchain_process_dev": [_V, _V, _SZ, _SZ, _V, _V, _SZ, _PSZ, _PSZ, _V],
     "sdrg_rxchain_process": [_V, _V, _SZ, _SZ, _V, _V, _SZ, _PSZ, _PSZ],
     "sdrg_kernel_launch_count": [C.POINTER(C.c_uint64)],
+    "sdrg_profile_enable": [_I],
+    "sdrg_profile_read": [_I, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
 }
 
 _lib = None
@@ -127,6 +129,20 @@ def check(rc):
 
 def call(name, *args):
     check(getattr(load(), name)(*args))
+
+
+KERNEL_IQBB_ACCUM, KERNEL_IQBB_FINALIZE, KERNEL_OLA, KERNEL_BANK = 1, 2, 3, 4
+
+
+def profile_enable(on):
+    call("sdrg_profile_enable", int(bool(on)))
+
+
+def profile_read(kind):
+    """(total device ms, launches) of the kernels of `kind` since the last read."""
+    ms, n = C.c_double(0), C.c_uint64(0)
+    call("sdrg_profile_read", int(kind), C.byref(ms), C.byref(n))
+    return ms.value, n.value
 
 
 def kernel_launch_count():

@@ -5,7 +5,7 @@
 // src/freqshift.hh:97-99: _lut_count) becomes
 //   device: the last L-1 input samples (double buffered), the open window's partial sum
 //           (slot 0 of the double-buffered accumulator array)
-//   host  : r0 = position inside the open window, first = "no sample seen yet", phase0 = NCO phase
+//   host  : consumed = samples since config() (fixes the window grid), phase0 = NCO phase
 // all of which advance in closed form with the number of samples consumed.
 #include "iqbb_kernels.cuh"
 
@@ -31,6 +31,36 @@ int set_error(int code, const char *fmt, ...) {
   return code;
 }
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-kernel timing (CUDA events on the launching stream) -----------------------------
+struct ProfSpan { cudaEvent_t a, b; int kind; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof_spans;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {   // records [begin, end) around one kernel launch when profiling is on
+  cudaStream_t st; int idx = -1;
+  ProfScope(int kind, cudaStream_t s) : st(s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfSpan sp{prof_event(), prof_event(), kind};
+    cudaEventRecord(sp.a, st);
+    g_prof_spans.push_back(sp);
+    idx = (int)g_prof_spans.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof_spans[idx].b, st);
+  }
+};
 
 // ---- managed buffers ---------------------------------------------------------------------------
 struct ManagedBuffer {
@@ -73,8 +103,7 @@ struct sdrg_iqbb {
   uint32_t acc_dirty[2] = {0, 0};
   uint32_t taps_len = 1, hist_len = 0;
   // stream position
-  uint32_t r0 = 0, phase0 = 0;
-  bool first = true;
+  uint32_t phase0 = 0;
   int parity = 0;
   uint64_t consumed = 0, produced = 0;
   // staging for the host-pointer entry points
@@ -123,17 +152,21 @@ int grow(void **p, size_t *cap, size_t need) {
 
 void free_dev(void **p) { if (*p) { cudaFree(*p); *p = nullptr; } }
 
-// outputs delivered by the next n samples, and the stream position afterwards
-struct Advance { uint64_t n_out; uint32_t r0_after; uint32_t e0; };
+// Window grid in closed form.  With c = samples consumed since config(), global
+// sample n carries the window counter q(n) = max(n,1)-1 (window 0 holds ss+1 samples because
+// _sample_count is incremented after the test, baseband.hh:200,212-217); a window completes at every
+// n >= 1 with n % ss == 0.  ss == 1 degenerates to one output per sample (baseband.hh:218-219).
+struct Advance { uint64_t n_out; uint32_t r0; uint32_t first; uint32_t e0; };
+uint64_t windows_done(uint64_t c, uint64_t ss) { return ss == 1 ? c : (c ? (c - 1) / ss : 0); }
 Advance advance(const sdrg_iqbb *h, uint64_t n) {
-  Advance a{0, h->r0, 0};
-  const uint64_t ss = h->d.sub_sample;
-  if (n == 0) return a;
-  const bool first = h->first && ss > 1;
-  const uint64_t q_last = (uint64_t)h->r0 + (n - 1) - ((first && n > 1) ? 1 : 0);
-  a.n_out = (q_last + 1) / ss;
-  a.r0_after = (uint32_t)((q_last + 1) % ss);
-  a.e0 = (uint32_t)(ss - 1 - h->r0 + (first ? 1 : 0));
+  const uint64_t ss = h->d.sub_sample, c = h->consumed;
+  Advance a{};
+  a.n_out = windows_done(c + n, ss) - windows_done(c, ss);
+  if (ss == 1) { a.r0 = 0; a.first = 0; a.e0 = 0; return a; }
+  a.first = c == 0 ? 1u : 0u;
+  a.r0 = c ? (uint32_t)((c - 1) % ss) : 0u;
+  const uint64_t lo = c ? c : 1;                           // first global index that can complete
+  a.e0 = (uint32_t)(((lo + ss - 1) / ss) * ss - c);
   return a;
 }
 
@@ -199,7 +232,7 @@ int ensure_acc(sdrg_iqbb *h, size_t slots) {
 }
 
 void reset_stream_state(sdrg_iqbb *h) {
-  h->r0 = 0; h->phase0 = 0; h->first = true; h->consumed = 0; h->produced = 0;
+  h->phase0 = 0; h->consumed = 0; h->produced = 0;
 }
 
 // config()-time recomputation (baseband.hh:156-194): host part
@@ -247,17 +280,19 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   int rc = ensure_acc(h, adv.n_out + 2);
   if (rc) return rc;
   const int p = h->parity, q = p ^ 1;
-  const bool first = h->first && h->d.sub_sample > 1;
   IqbbAccumArgs a{};
   a.x = d_in; a.hist_in = h->d_hist[p]; a.hist_out = h->d_hist[q];
   a.taps = h->d_taps; a.lut = h->d_lut;
   a.acc_cur = h->d_acc[p]; a.acc_next = h->d_acc[q];
   a.n = n; a.taps_len = h->taps_len; a.hist_len = h->hist_len;
-  a.ss = (uint32_t)h->d.sub_sample; a.r0 = h->r0; a.first = first ? 1u : 0u;
+  a.ss = (uint32_t)h->d.sub_sample; a.r0 = adv.r0; a.first = adv.first;
   a.phase0 = h->phase0; a.inc = (uint32_t)(h->d.lut_inc & 0x7fffu); a.nco = h->d.lut_inc != 0 ? 1u : 0u;
   a.neg = h->d.negative ? 1u : 0u;
   a.zero_next = h->acc_dirty[q];
-  rc = launch_iqbb_accum(h->d.scalar, a, st);
+  {
+    ProfScope ps(SDRG_KERNEL_IQBB_ACCUM, st);
+    rc = launch_iqbb_accum(h->d.scalar, a, st);
+  }
   if (rc) return rc;
   IqbbFinalizeArgs f{};
   f.acc_cur = h->d_acc[p]; f.acc_next = h->d_acc[q];
@@ -265,13 +300,14 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   f.fm_last_in = fm_last_in; f.fm_last_out = fm_last_out;
   f.n_out = (uint32_t)adv.n_out; f.ss = a.ss; f.demod = (uint32_t)demod; f.e0 = adv.e0;
   f.seg = seg; f.in_place = (uint32_t)in_place;
-  rc = launch_iqbb_finalize(h->d.scalar, f, st);
+  {
+    ProfScope ps(SDRG_KERNEL_IQBB_FINALIZE, st);
+    rc = launch_iqbb_finalize(h->d.scalar, f, st);
+  }
   if (rc) return rc;
   h->acc_dirty[p] = (uint32_t)adv.n_out + 1;   // slots this call touched
   h->acc_dirty[q] = 1;                         // the carry
   h->parity = q;
-  h->r0 = adv.r0_after;
-  h->first = false;
   h->phase0 = (uint32_t)((h->phase0 + (uint64_t)n * (h->d.lut_inc & 0x7fffu)) & 0x7fffu);
   h->consumed += n; h->produced += adv.n_out;
   return SDRG_OK;
@@ -317,6 +353,28 @@ int sdrg_device_synchronize(void) { SDRG_CUDA(cudaDeviceSynchronize()); return S
 int sdrg_kernel_launch_count(uint64_t *count) {
   if (!count) return set_error(SDRG_ERR_ARG, "null argument");
   *count = g_launches.load();
+  return SDRG_OK;
+}
+
+int sdrg_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return SDRG_OK;
+}
+int sdrg_profile_read(int kind, double *total_ms, uint64_t *launches) {
+  if (!total_ms || !launches) return set_error(SDRG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  *total_ms = 0; *launches = 0;
+  std::vector<ProfSpan> keep;
+  for (const ProfSpan &sp : g_prof_spans) {
+    if (sp.kind != kind) { keep.push_back(sp); continue; }
+    SDRG_CUDA(cudaEventSynchronize(sp.b));
+    float ms = 0;
+    SDRG_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    *total_ms += ms; *launches += 1;
+    g_prof_pool.push_back(sp.a); g_prof_pool.push_back(sp.b);
+  }
+  g_prof_spans.swap(keep);
   return SDRG_OK;
 }
 
