@@ -92,6 +92,12 @@ int sdrg_iqbb_configure(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out);
  * (sdrg_iqbb_get_info) on a machine without a GPU. */
 int sdrg_iqbb_design(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out);
 
+/* SDRG_T_F32 only: which accumulate kernel config() selects.  0 = auto (folded when
+ * sub_sample >= max(32, order-1), else direct), 1 = direct (sample-by-sample FIR, FMA-bound),
+ * 2 = folded (one weight per input sample, HBM-bound; SDRG_ERR_CONFIG at config() if not eligible).
+ * Must be called before config(). */
+int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode);
+
 /* What config() derived; kernel/lut are written only when non-NULL (order / 128 int32 pairs, resp.
  * float pairs for SDRG_T_F32). */
 typedef struct {

@@ -72,6 +72,7 @@ SIGNATURES = {
     "sdrg_iqbb_set_subsample": [_V, _SZ],
     "sdrg_iqbb_set_output_sample_rate": [_V, _D],
     "sdrg_iqbb_configure": [_V, _PCFG, _PCFG],
+    "sdrg_iqbb_set_float_path": [_V, _I],
     "sdrg_iqbb_design": [_V, _PCFG, _PCFG],
     "sdrg_iqbb_get_info": [_V, C.POINTER(IqbbInfo), _V, _V],
     "sdrg_iqbb_process": [_V, _V, _SZ, _V, _SZ, _PSZ],

@@ -102,6 +102,10 @@ struct sdrg_iqbb {
   size_t acc_cap = 0;
   uint32_t acc_dirty[2] = {0, 0};
   uint32_t taps_len = 1, hist_len = 0;
+  // folded float path (iqbb_fold_kernels.cu)
+  int float_path = 0;                  // 0 auto, 1 direct, 2 folded
+  bool fold = false;
+  void *d_tab_a = nullptr, *d_tab_u = nullptr;
   // stream position
   uint32_t phase0 = 0;
   int parity = 0;
@@ -170,6 +174,48 @@ Advance advance(const sdrg_iqbb *h, uint64_t n) {
   return a;
 }
 
+// Folded float path: A(a) and U(r,e) in double on the host (see iqbb_fold_kernels.cu).
+int upload_fold_tables(sdrg_iqbb *h) {
+  const IqbbDesign &d = h->d;
+  free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
+  const size_t L = d.order, ss = d.sub_sample;
+  const bool eligible = d.scalar == SDRG_T_F32 && ss >= 32 && ss + 1 >= L;
+  if (h->float_path == 2 && !eligible && d.scalar == SDRG_T_F32)
+    return set_error(SDRG_ERR_CONFIG, "IQBaseBand<float>: folded path needs sub_sample >= max(32, order-1) (ss=%zu, order=%zu)", ss, L);
+  h->fold = eligible && h->float_path != 1;
+  if (!h->fold) return SDRG_OK;
+  const bool nco = d.lut_inc != 0, neg = d.negative;
+  const uint64_t inc = d.lut_inc & 0x7fffu;
+  std::vector<float> A(2 * 128), U(2 * 256 * L);
+  for (size_t a = 0; a < 128; ++a) {
+    A[2 * a] = nco ? (float)d.lutd_re[a] : 1.0f;
+    A[2 * a + 1] = nco ? (float)(neg ? -d.lutd_im[a] : d.lutd_im[a]) : 0.0f;
+  }
+  std::vector<double> br(L), bi(L);
+  for (size_t r = 0; r < 256; ++r) {
+    for (size_t j = 0; j < L; ++j) {           // B(r, j)
+      if (!nco) { br[j] = 1.0; bi[j] = 0.0; continue; }
+      const uint64_t s = (r + j * inc) >> 8;
+      const size_t idx = neg ? (size_t)((127 + 128 - (s % 128)) % 128) : (size_t)(s % 128);
+      br[j] = d.lutd_re[idx]; bi[j] = d.lutd_im[idx];
+    }
+    for (size_t e = 0; e < L; ++e) {
+      double sr = 0, si = 0;
+      for (size_t j = 0; j + e < L; ++j) {
+        const double kr = d.kd_re[L - 1 - e - j], ki = d.kd_im[L - 1 - e - j];
+        sr += br[j] * kr - bi[j] * ki;
+        si += br[j] * ki + bi[j] * kr;
+      }
+      U[2 * (r * L + e)] = (float)sr; U[2 * (r * L + e) + 1] = (float)si;
+    }
+  }
+  SDRG_CUDA(cudaMalloc(&h->d_tab_a, A.size() * sizeof(float)));
+  SDRG_CUDA(cudaMemcpy(h->d_tab_a, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SDRG_CUDA(cudaMalloc(&h->d_tab_u, U.size() * sizeof(float)));
+  SDRG_CUDA(cudaMemcpy(h->d_tab_u, U.data(), U.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SDRG_OK;
+}
+
 int upload_design(sdrg_iqbb *h) {
   const IqbbDesign &d = h->d;
   const size_t L = d.order;
@@ -203,6 +249,8 @@ int upload_design(sdrg_iqbb *h) {
     SDRG_CUDA(cudaMalloc(&h->d_lut, lut.size() * sizeof(int32_t)));
     SDRG_CUDA(cudaMemcpy(h->d_lut, lut.data(), lut.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
+  int rc_fold = upload_fold_tables(h);
+  if (rc_fold) return rc_fold;
   h->hist_len = h->taps_len - 1;
   const size_t hb = (h->hist_len ? h->hist_len : 1) * sample_bytes(d.scalar);
   for (int k = 0; k < 2; ++k) {
@@ -222,7 +270,7 @@ int ensure_acc(sdrg_iqbb *h, size_t slots) {
   SDRG_CUDA(cudaMemset(n1, 0, cap * acc_bytes()));
   if (h->d_acc[0]) {   // keep the open window (slot 0 of the current parity)
     SDRG_CUDA(cudaDeviceSynchronize());
-    SDRG_CUDA(cudaMemcpy(h->parity == 0 ? n0 : n1, h->d_acc[h->parity], acc_bytes(), cudaMemcpyDeviceToDevice));
+    SDRG_CUDA(cudaMemcpy(h->parity == 0 ? n0 : n1, h->d_acc[h->parity], 2 * acc_bytes(), cudaMemcpyDeviceToDevice));
     cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]);
   }
   h->d_acc[0] = n0; h->d_acc[1] = n1;
@@ -260,7 +308,7 @@ int reconfigure(sdrg_iqbb *h) {
   IqbbDesign &d = h->d;
   rc = upload_design(h);
   if (rc) return rc;
-  rc = ensure_acc(h, d.out_bs + 2);
+  rc = ensure_acc(h, d.out_bs + 3);
   if (rc) return rc;
   SDRG_CUDA(cudaMemset(h->d_acc[0], 0, h->acc_cap * acc_bytes()));
   SDRG_CUDA(cudaMemset(h->d_acc[1], 0, h->acc_cap * acc_bytes()));
@@ -277,7 +325,7 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
              uint64_t *n_out) {
   const Advance adv = advance(h, n);
   *n_out = adv.n_out;
-  int rc = ensure_acc(h, adv.n_out + 2);
+  int rc = ensure_acc(h, adv.n_out + 3);
   if (rc) return rc;
   const int p = h->parity, q = p ^ 1;
   IqbbAccumArgs a{};
@@ -289,7 +337,16 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   a.phase0 = h->phase0; a.inc = (uint32_t)(h->d.lut_inc & 0x7fffu); a.nco = h->d.lut_inc != 0 ? 1u : 0u;
   a.neg = h->d.negative ? 1u : 0u;
   a.zero_next = h->acc_dirty[q];
-  {
+  if (h->fold) {
+    IqbbFoldArgs fa{};
+    fa.x = d_in; fa.acc_cur = a.acc_cur; fa.acc_next = a.acc_next;
+    fa.tab_a = (const float2 *)h->d_tab_a; fa.tab_u = (const float2 *)h->d_tab_u;
+    fa.n = n; fa.taps_len = (uint32_t)h->d.order; fa.ss = a.ss; fa.r0 = a.r0; fa.first = a.first;
+    fa.phase0 = a.nco ? a.phase0 : 0u; fa.inc = a.nco ? a.inc : 0u;
+    fa.zero_next = a.zero_next; fa.seg = 2048;
+    ProfScope ps(SDRG_KERNEL_IQBB_ACCUM, st);
+    rc = launch_iqbb_fold(fa, st);
+  } else {
     ProfScope ps(SDRG_KERNEL_IQBB_ACCUM, st);
     rc = launch_iqbb_accum(h->d.scalar, a, st);
   }
@@ -305,8 +362,8 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
     rc = launch_iqbb_finalize(h->d.scalar, f, st);
   }
   if (rc) return rc;
-  h->acc_dirty[p] = (uint32_t)adv.n_out + 1;   // slots this call touched
-  h->acc_dirty[q] = 1;                         // the carry
+  h->acc_dirty[p] = (uint32_t)adv.n_out + 2;   // slots this call touched
+  h->acc_dirty[q] = 2;                         // the carry
   h->parity = q;
   h->phase0 = (uint32_t)((h->phase0 + (uint64_t)n * (h->d.lut_inc & 0x7fffu)) & 0x7fffu);
   h->consumed += n; h->produced += adv.n_out;
@@ -508,6 +565,7 @@ int sdrg_iqbb_destroy(sdrg_iqbb *h) {
   free_dev(&h->d_taps); free_dev(&h->d_lut);
   free_dev(&h->d_hist[0]); free_dev(&h->d_hist[1]);
   free_dev(&h->d_acc[0]); free_dev(&h->d_acc[1]);
+  free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
   free_dev(&h->d_in); free_dev(&h->d_out);
   delete h;
   return SDRG_OK;
@@ -541,6 +599,11 @@ int sdrg_iqbb_set_center_frequency(sdrg_iqbb *h, double Fc) {
   h->d.freq_shift = double(h->d.Fc);       // setFrequencyShift(_Fc) receives the int32 member
   design_lut_increment(h->d, h->nco_Fs);
   h->phase0 = 0;                           // _lut_count = 0
+  if (h->configured && h->d.scalar == SDRG_T_F32) {   // the folded tables embed the NCO increment
+    SDRG_CUDA(cudaSetDevice(h->device));
+    SDRG_CUDA(cudaDeviceSynchronize());
+    return upload_fold_tables(h);
+  }
   return SDRG_OK;
 }
 int sdrg_iqbb_set_filter_frequency(sdrg_iqbb *h, double Ff) {
@@ -578,6 +641,14 @@ int sdrg_iqbb_set_output_sample_rate(sdrg_iqbb *h, double oFs) {
   SDRG_CUDA(cudaSetDevice(h->device));
   SDRG_CUDA(cudaDeviceSynchronize());
   return reconfigure(h);
+}
+
+int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (mode < 0 || mode > 2) return set_error(SDRG_ERR_ARG, "IQBaseBand: float path must be 0 (auto), 1 (direct) or 2 (folded)");
+  if (h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: select the float path before config()");
+  h->float_path = mode;
+  return SDRG_OK;
 }
 
 int sdrg_iqbb_configure(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out) {

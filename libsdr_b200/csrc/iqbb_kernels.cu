@@ -353,7 +353,10 @@ __global__ void __launch_bounds__(256) iqbb_finalize_kernel(const IqbbFinalizeAr
   typedef Fin<SCALAR> F;
   const typename F::Acc *acc = (const typename F::Acc *)a.acc_cur;
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) ((typename F::Acc *)a.acc_next)[0] = acc[a.n_out];       // carry the open window
+  if (j == 0) {   // carry the open window and (folded float path) the tails already sent past it
+    ((typename F::Acc *)a.acc_next)[0] = acc[a.n_out];
+    ((typename F::Acc *)a.acc_next)[1] = acc[a.n_out + 1];
+  }
   if (a.demod == SDRG_DEMOD_FM && j == 0) {                             // carried FM angle
     typename F::Last last = *(const typename F::Last *)a.fm_last_in;
     for (int64_t k = (int64_t)a.n_out - 1; k >= 0; --k) {

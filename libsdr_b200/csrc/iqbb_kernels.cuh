@@ -31,10 +31,26 @@ struct IqbbAccumArgs {
   uint32_t    zero_next;
 };
 
+// One process() call of the folded float kernel (iqbb_fold_kernels.cu)
+struct IqbbFoldArgs {
+  const void   *x;          // n float2 samples
+  void         *acc_cur;    // float2 window accumulators; slots n_out and n_out+1 stay open
+  void         *acc_next;
+  const float2 *tab_a;      // A(a), 128 entries
+  const float2 *tab_u;      // U(r,e), 256 rows of taps_len entries
+  uint32_t      n;
+  uint32_t      taps_len;   // L
+  uint32_t      ss;
+  uint32_t      r0, first;
+  uint32_t      phase0, inc;
+  uint32_t      zero_next;
+  uint32_t      seg;        // samples per warp segment (multiple of 32)
+};
+
 // finalize (+ optional demodulation) of the completed windows of one call
 struct IqbbFinalizeArgs {
   const void *acc_cur;    // n_out completed slots followed by the open one
-  void       *acc_next;   // slot 0 receives the carry
+  void       *acc_next;   // slots 0 and 1 receive the carry (open window, and the one after it)
   void       *bb_out;     // complex Scalar[n_out] or null
   void       *audio_out;  // demod output or null
   const void *fm_last_in; // carried FM angle (int16 as int32 / double), device scalar
@@ -49,6 +65,7 @@ struct IqbbFinalizeArgs {
 
 int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st);
 int launch_iqbb_finalize(int scalar, const IqbbFinalizeArgs &a, cudaStream_t st);
+int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st);
 
 // stand-alone demodulators (demod_kernels.cu)
 int launch_fmdemod(int scalar, const void *in, size_t n, void *out, const void *last_in, void *last_out,

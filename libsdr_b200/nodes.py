@@ -75,6 +75,10 @@ class IQBaseBand:
     def setSubsample(self, ss): _lib.call("sdrg_iqbb_set_subsample", self._h, int(ss))
     def setOutputSampleRate(self, fs): _lib.call("sdrg_iqbb_set_output_sample_rate", self._h, float(fs))
 
+    def setFloatPath(self, mode):
+        """f32 only: 0 auto, 1 direct kernel, 2 folded kernel (before config())."""
+        _lib.call("sdrg_iqbb_set_float_path", self._h, int(mode))
+
     def config(self, src_cfg=None, *, type=None, sample_rate=0.0, buffer_size=0, num_buffers=1):
         """config(const Config&) (baseband.hh:115-132). Raises ConfigError on a type mismatch."""
         if src_cfg is None:

@@ -18,13 +18,15 @@ FLOAT_TOL = 1e-5
 OSC = {"s16": orc.S16, "s8": orc.S8, "f32": orc.F32}
 
 
-def gpu_bb(g_or_cfg, Fs=None, bs=None):
+def gpu_bb(g_or_cfg, Fs=None, bs=None, float_path=0):
     c = g_or_cfg
     bb = IQBaseBand(str(c["scalar"]), float(c["Fc"]), float(c["Ff"]), float(c["width"]), int(c["order"]),
                     int(c["sub_sample_arg"] if "sub_sample_arg" in c else c["sub_sample"]), float(c["oFs"]))
     if "setcf" in c and int(c["setcf"]):
         bb.setCenterFrequency(float(c["Fc"]))
         bb.setFilterFrequency(float(c["Ff"]))
+    if float_path:
+        bb.setFloatPath(float_path)
     bb.config(sample_rate=float(c["Fs"]) if Fs is None else Fs, buffer_size=int(c["buffer_size"]) if bs is None else bs)
     return bb
 
@@ -223,8 +225,8 @@ def test_error_behaviour():
 
 # ---- float path (defined by the restatement; tolerance 1e-5 relative RMS) -----------------------
 
-def _float_case(cfg, x, bs, demod=DEMOD_FM):
-    g, o = gpu_bb(cfg, bs=bs), orc_bb(cfg, bs=bs)
+def _float_case(cfg, x, bs, demod=DEMOD_FM, path=0):
+    g, o = gpu_bb(cfg, bs=bs, float_path=path), orc_bb(cfg, bs=bs)
     chain = RxChain(g, demod)
     yb, ya, counts = chain.process(x, bs)
     ofm = orc.FMDemod(orc.F32)
@@ -248,19 +250,54 @@ def _float_case(cfg, x, bs, demod=DEMOD_FM):
     return e_bb, e_a
 
 
-def test_c2_float_chain():
+PATHS = [(1, "direct"), (2, "folded")]
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["direct", "folded"])
+def test_c2_float_chain(path):
     cfg = dict(synth.C2)
     x = synth.c2_input(2 << 20)
-    _float_case(cfg, x, 1 << 20, DEMOD_FM)
+    e = _float_case(cfg, x, 1 << 20, DEMOD_FM, path)
+    print("c2 rel-rms (bb, fm):", e)
 
 
-@pytest.mark.parametrize("demod", [DEMOD_AM, DEMOD_USB])
-def test_float_small_configs(demod):
+@pytest.mark.parametrize("path", [1, 2], ids=["direct", "folded"])
+@pytest.mark.parametrize("demod", [DEMOD_AM, DEMOD_USB, DEMOD_FM])
+def test_float_small_configs(demod, path):
     cfg = dict(scalar="f32", Fs=2.4e6, Fc=-100e3, Ff=-100e3, width=30e3, order=21, sub_sample=1, oFs=48000.0)
     x = synth.iq_f32(200000, 2.4e6, [(0.5, -103e3, 0.0), (0.2, 500e3, 1.0)], 0.01, 3)
-    _float_case(cfg, x, 50000, demod)
-    cfg.update(sub_sample=7, oFs=0.0, order=33)
-    _float_case(cfg, x, 40000, demod)
+    _float_case(cfg, x, 50000, demod, path)          # ss=50, negative shift
+    cfg.update(Fc=0.0, Ff=0.0)
+    _float_case(cfg, x, 50000, demod, path)          # lut_inc == 0: mixer bypassed
+    if path == 1:
+        cfg.update(Fc=77e3, Ff=60e3, sub_sample=7, oFs=0.0, order=33)   # ss < order-1: direct only
+        _float_case(cfg, x, 40000, demod, path)
+
+
+@pytest.mark.parametrize("ss,order", [(32, 33), (63, 64), (64, 64), (100, 2), (416, 1), (5000, 64), (300000, 128)])
+def test_float_folded_geometry(ss, order):
+    """Folded kernel across window/segment geometries (window << segment, window >> segment,
+    ss == order-1, order 1), ragged multi-call streams."""
+    cfg = dict(scalar="f32", Fs=20e6, Fc=1.23e6, Ff=1.2e6, width=200e3, order=order, sub_sample=ss, oFs=0.0)
+    n = 700000
+    x = synth.iq_f32(n, 20e6, [(0.5, 1.25e6, 0.0), (0.3, -4e6, 1.0)], 0.02, 11)
+    g, o = gpu_bb(cfg, bs=n, float_path=2), orc_bb(cfg, bs=n)
+    cuts = [0, 1, 31, 32, 33, 2047, 2048, 2049, 100000, 100001, 400000, n]
+    ys, os_ = [], []
+    for s, e in zip(cuts[:-1], cuts[1:]):
+        ys.append(g.process(x[s:e])); os_.append(o.process(x[s:e]))
+        assert ys[-1].shape == os_[-1].shape
+    y, ob = np.concatenate(ys), np.concatenate(os_)
+    if ob.shape[0]:
+        e = rel_rms(y.astype(np.float64).view(np.complex128), ob.astype(np.float64).view(np.complex128))
+        assert e < FLOAT_TOL, e
+
+
+def test_float_folded_rejects_ineligible():
+    bb = IQBaseBand("f32", 0.0, 0.0, 1e5, 64, 7, 0.0)
+    bb.setFloatPath(2)
+    with pytest.raises(ConfigError):
+        bb.config(sample_rate=2.4e6, buffer_size=4096)
 
 
 # ---- (3) size-independent properties at full size ------------------------------------------------
