@@ -180,7 +180,7 @@ int upload_fold_tables(sdrg_iqbb *h) {
   free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
   const size_t L = d.order, ss = d.sub_sample;
   const bool eligible = d.scalar == SDRG_T_F32 && ss >= 32 && ss + 1 >= L;
-  if (h->float_path == 2 && !eligible && d.scalar == SDRG_T_F32)
+  if (h->float_path >= 2 && !eligible && d.scalar == SDRG_T_F32)
     return set_error(SDRG_ERR_CONFIG, "IQBaseBand<float>: folded path needs sub_sample >= max(32, order-1) (ss=%zu, order=%zu)", ss, L);
   h->fold = eligible && h->float_path != 1;
   if (!h->fold) return SDRG_OK;
@@ -343,7 +343,7 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
     fa.tab_a = (const float2 *)h->d_tab_a; fa.tab_u = (const float2 *)h->d_tab_u;
     fa.n = n; fa.taps_len = (uint32_t)h->d.order; fa.ss = a.ss; fa.r0 = a.r0; fa.first = a.first;
     fa.phase0 = a.nco ? a.phase0 : 0u; fa.inc = a.nco ? a.inc : 0u;
-    fa.zero_next = a.zero_next; fa.seg = 2048;
+    fa.zero_next = a.zero_next; fa.variant = h->float_path == 3 ? 2u : 0u;
     ProfScope ps(SDRG_KERNEL_IQBB_ACCUM, st);
     rc = launch_iqbb_fold(fa, st);
   } else {
@@ -645,7 +645,7 @@ int sdrg_iqbb_set_output_sample_rate(sdrg_iqbb *h, double oFs) {
 
 int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
-  if (mode < 0 || mode > 2) return set_error(SDRG_ERR_ARG, "IQBaseBand: float path must be 0 (auto), 1 (direct) or 2 (folded)");
+  if (mode < 0 || mode > 3) return set_error(SDRG_ERR_ARG, "IQBaseBand: float path must be 0 (auto), 1 (direct), 2 (folded) or 3 (folded, TMA staging)");
   if (h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: select the float path before config()");
   h->float_path = mode;
   return SDRG_OK;

@@ -10,14 +10,21 @@
 //                      T_e(p) = A(a_b) * U(r_b, e),   phi_b = phase at the next window's first sample
 //     U(r,e) = sum_{j=0}^{L-1-e} B(r,j) k[L-1-e-j]       (256 x L table, built on the host in double)
 // Each sample is read ONCE and contributes (G - T) x to its own window and T x to the next one
-// (requires ss >= L-1); no halo re-reads, no FIR history.  ~10 flop and 8 bytes per input sample.
+// (requires ss >= L-1); no halo re-reads, no FIR history: 8 bytes and ~5 flop per sample.
 //
-// Mapping: a warp owns a contiguous segment of the call's samples and walks the windows that cross
-// it; lanes stride over the samples (coalesced 8-byte loads, 4 independent loads in flight per
-// lane), keep per-lane partial sums, and only at a window end reduce with shuffles and issue one
-// RED.ADD per component into the per-call window accumulators (same finalize kernel as the direct
-// path).  The "next window" partials simply become the running partials of the next window.
+// Mapping.  The unit of work is a chunk: a window (clipped to the call), or a <= `part`-sample
+// piece of a long window.  A warp owns a run of consecutive chunks and walks each in steps of 32
+// lanes aligned to the chunk start.  Lane l sees samples l, l+32, ...: its low phase byte r
+// advances by 32*inc per step and so cycles with period <= 8 steps; the eight U(r,0) values a lane
+// needs for a chunk live in registers and the window sum factorises per residue u = step mod 8:
+//     S = sum_u H_u * ( sum_{steps = u mod 8} A(a_p) x[p] )  -  (tails sent ahead)  +  (tails received)
+// i.e. per sample: one 8-byte streaming load, one lookup in a 1 KB table, one complex FMA.  Loads
+// are issued 8 steps (2 KB per warp) ahead of their use.  Partial sums stay in registers; at a
+// chunk end the warp reduces with shuffles and issues one RED.ADD per component into the per-call
+// accumulators (finalized by iqbb_finalize_kernel); tails sent ahead are carried in registers into
+// the next window when the same warp processes it.
 #include "iqbb_kernels.cuh"
+#include <cstdlib>
 
 namespace sdrg {
 namespace {
@@ -30,6 +37,12 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p) {
   float2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
+}
+// bulk L2 prefetch of [p, p + bytes): one instruction, no registers held while the data is in flight
+__device__ __forceinline__ void prefetch_l2(const float2 *lo, const float2 *hi) {
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(lo) + 15) & ~uintptr_t(15);
+  const uintptr_t b = reinterpret_cast<uintptr_t>(hi) & ~uintptr_t(15);
+  if (b > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)(b - a)) : "memory");
 }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -48,7 +61,55 @@ __device__ __forceinline__ void flush(float *acc, uint32_t slot, float2 v, int l
   if (lane == 0 && (sr != 0.f || si != 0.f)) { atomicAdd(acc + 2 * (size_t)slot, sr); atomicAdd(acc + 2 * (size_t)slot + 1, si); }
 }
 
-__global__ void __launch_bounds__(kFoldThreads) iqbb_fold_f32_kernel(const IqbbFoldArgs a) {
+// Per-warp staging of window partials: row w holds the 32 per-lane partial sums of the w-th window
+// this warp finished; once 32 rows are full lane l sums row l (one LDS.64 per element, rows padded
+// to 33 to stay conflict free) and issues the RED.ADDs for its window.  This replaces a 5-step
+// shuffle reduction per component per window by ~3 instructions per window.
+constexpr int kStageRows = 32, kStagePitch = 33;
+
+struct WarpStage {
+  float2 *rows;      // [kStageRows][kStagePitch]
+  uint32_t my_slot;  // lane l: slot of row l
+  uint32_t count;
+  __device__ __forceinline__ void push(float2 v, uint32_t slot, int lane, float *acc_out) {
+    rows[count * kStagePitch + lane] = v;
+    if ((uint32_t)lane == count) my_slot = slot;
+    if (++count == kStageRows) drain(lane, acc_out);
+  }
+  __device__ __forceinline__ void drain(int lane, float *acc_out) {
+    __syncwarp();
+    if ((uint32_t)lane < count) {
+      float sr = 0.f, si = 0.f;
+      const float2 *r = rows + lane * kStagePitch;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) { const float2 v = r[i]; sr += v.x; si += v.y; }
+      if (sr != 0.f || si != 0.f) { atomicAdd(acc_out + 2 * (size_t)my_slot, sr); atomicAdd(acc_out + 2 * (size_t)my_slot + 1, si); }
+    }
+    __syncwarp();
+    count = 0;
+  }
+};
+
+// chunk id -> (slot, first sample, length, tail start); false for an empty piece
+struct Chunk { uint32_t s; int c_lo, len, t_lo, full_end; };
+__device__ __forceinline__ bool chunk_of(const IqbbFoldArgs &a, uint32_t id, int win_off, int L1, Chunk &c) {
+  const uint32_t s = a.cpw == 1 ? id : id / a.cpw, part = a.cpw == 1 ? 0u : id % a.cpw;
+  c.s = s;
+  c.full_end = (int)((s + 1) * a.ss) + win_off;                          // exclusive, may exceed n
+  const int w_lo = s == 0 ? 0 : (int)(s * a.ss) + win_off;
+  const int w_hi = min(c.full_end, (int)a.n);
+  c.c_lo = w_lo + (int)(part * a.part);
+  if (c.c_lo >= w_hi) return false;
+  c.len = min(c.c_lo + (int)a.part, w_hi) - c.c_lo;
+  c.t_lo = max(0, min(c.len, c.full_end - L1 - c.c_lo));                 // samples >= t_lo send a tail ahead
+  return true;
+}
+
+// Persistent grid (one CTA per resident slot); chunk ids are dealt round-robin to the warps of the
+// whole grid, so that at any moment the running warps read ONE compact, linearly advancing region
+// of the input (DRAM row locality, like a grid-stride loop) instead of thousands of separate fronts.
+__global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_kernel(const IqbbFoldArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ float2 sA[128];
   __shared__ float2 sH[256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -60,74 +121,282 @@ __global__ void __launch_bounds__(kFoldThreads) iqbb_fold_f32_kernel(const IqbbF
   sH[tid] = a.tab_u[(size_t)tid * a.taps_len];              // U(r, 0)
   __syncthreads();
 
-  const uint64_t seg_lo64 = ((uint64_t)blockIdx.x * kFoldWarps + warp) * a.seg;
-  if (seg_lo64 >= a.n) return;
-  const uint32_t seg_lo = (uint32_t)seg_lo64;
-  const uint32_t seg_hi = (uint32_t)min((uint64_t)a.n, seg_lo64 + a.seg);
+  const uint32_t total_warps = gridDim.x * kFoldWarps;
+  const uint32_t wg = warp * gridDim.x + blockIdx.x;        // neighbouring CTAs take neighbouring chunks
+  if (wg >= a.n_chunks) return;
+
   const float2 *__restrict__ x = (const float2 *)a.x;
   float *acc_out = (float *)a.acc_cur;
-  const int64_t L1 = (int64_t)a.taps_len - 1;
-  const int64_t win_off = (int64_t)a.first - (int64_t)a.r0;  // end(s) = (s+1)*ss + win_off
+  WarpStage stage{(float2 *)dyn_smem + (size_t)warp * kStageRows * kStagePitch, 0u, 0u};
+  const int L1 = (int)a.taps_len - 1;
+  const int win_off = (int)a.first - (int)a.r0;   // begin(s) = s*ss + win_off (s>0), end(s) = (s+1)*ss + win_off
+  const uint32_t inc32 = (32u * a.inc) & 0x7fffu, inc256 = (256u * a.inc) & 0x7fffu;
 
-  uint32_t s = (uint32_t)(((uint64_t)a.r0 + seg_lo - ((a.first && seg_lo > 0) ? 1u : 0u)) / a.ss);
-  float2 acc = make_float2(0.f, 0.f), nxt = make_float2(0.f, 0.f);
-  uint32_t i = seg_lo;
-  while (i < seg_hi) {
-    const int64_t full_end = (int64_t)((uint64_t)(s + 1) * a.ss) + win_off;   // exclusive, call-relative
-    const uint32_t wend = (uint32_t)min(full_end, (int64_t)seg_hi);
-    const int64_t tr_lo = full_end - L1;                                       // first sample with a tail
-    const uint32_t int_hi = (uint32_t)max((int64_t)i, min((int64_t)wend, tr_lo));
+  for (uint32_t id = wg; id < a.n_chunks; id += total_warps) {
+    Chunk c;
+    if (lane == 0 && id + total_warps < a.n_chunks) {       // next chunk of this warp -> L2, one instruction
+      Chunk nx;
+      if (chunk_of(a, id + total_warps, win_off, L1, nx)) prefetch_l2(x + nx.c_lo, x + nx.c_lo + nx.len);
+    }
+    if (!chunk_of(a, id, win_off, L1, c)) continue;
+    const int len = c.len;
+    uint32_t ph = (a.phase0 + (uint32_t)(c.c_lo + lane) * a.inc) & 0x7fffu;         // this lane's phase in step 0
+    float2 H[8], R[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { H[u] = sH[(ph + u * inc32) & 255u]; R[u] = make_float2(0.f, 0.f); }
+    const float2 *__restrict__ xc = x + c.c_lo + lane;
 
-    // interior samples: weight G(p) = A(a_p) U(r_p,0)
-    uint32_t j = i + lane;
-    for (; j + 96 < int_hi; j += 128) {
-      const float2 x0 = ld_stream(x + j), x1 = ld_stream(x + j + 32), x2 = ld_stream(x + j + 64), x3 = ld_stream(x + j + 96);
-      const uint32_t p0 = (a.phase0 + j * a.inc) & 0x7fffu, p1 = (p0 + 32 * a.inc) & 0x7fffu,
-                     p2 = (p0 + 64 * a.inc) & 0x7fffu, p3 = (p0 + 96 * a.inc) & 0x7fffu;
-      cfma(acc, cmul(sA[p0 >> 8], sH[p0 & 255]), x0);
-      cfma(acc, cmul(sA[p1 >> 8], sH[p1 & 255]), x1);
-      cfma(acc, cmul(sA[p2 >> 8], sH[p2 & 255]), x2);
-      cfma(acc, cmul(sA[p3 >> 8], sH[p3 & 255]), x3);
+    // every sample: R_u += A(a_p) x[p]   (its full weight G = H_u A)
+    int k = 0;
+    for (; k + 256 <= len; k += 256, ph = (ph + inc256) & 0x7fffu) {
+      float2 xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xv[u] = ld_stream(xc + k + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
     }
-    for (; j < int_hi; j += 32) {
-      const float2 x0 = ld_stream(x + j);
-      const uint32_t p0 = (a.phase0 + j * a.inc) & 0x7fffu;
-      cfma(acc, cmul(sA[p0 >> 8], sH[p0 & 255]), x0);
-    }
-    // trailing samples of the window: split between this window and the next
-    if ((int64_t)wend > tr_lo) {
-      const uint32_t pb = (a.phase0 + (uint32_t)full_end * a.inc) & 0x7fffu;
-      const float2 Ab = sA[pb >> 8];
-      const float2 *__restrict__ urow = a.tab_u + (size_t)(pb & 255) * a.taps_len;
-      for (j = int_hi + lane; j < wend; j += 32) {
-        const float2 x0 = ld_stream(x + j);
-        const uint32_t p0 = (a.phase0 + j * a.inc) & 0x7fffu;
-        const float2 g = cmul(sA[p0 >> 8], sH[p0 & 255]);
-        const float2 t = cmul(Ab, __ldg(urow + (uint32_t)(full_end - (int64_t)j)));
-        cfma(acc, make_float2(g.x - t.x, g.y - t.y), x0);
-        cfma(nxt, t, x0);
+    if (k < len) {                        // ragged last batch
+      const int rem = len - k;
+      float2 xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        xv[u] = make_float2(0.f, 0.f);
+        if (32 * u < rem && 32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (32 * u >= rem) break;
+        cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
       }
     }
-    i = wend;
-    if ((int64_t)wend == full_end) {       // window complete within this segment
-      flush(acc_out, s, acc, lane);
-      acc = nxt; nxt = make_float2(0.f, 0.f);
-      ++s;
+    // the last L-1 samples of the window also owe T_e x to the next window (re-read, L1/L2 resident)
+    float2 sent = make_float2(0.f, 0.f);
+    if (c.t_lo < len) {
+      const uint32_t pb = (a.phase0 + (uint32_t)c.full_end * a.inc) & 0x7fffu;
+      const float2 Ab = sA[pb >> 8];
+      const float2 *__restrict__ ue = a.tab_u + (size_t)(pb & 255u) * a.taps_len + (c.full_end - c.c_lo - lane);  // U(r_b, e), e = end - j
+      for (int j = c.t_lo + lane; j < len; j += 32)
+        cfma(sent, cmul(Ab, __ldg(ue - (j - lane))), __ldg(xc + (j - lane)));
     }
+    float2 tot = make_float2(-sent.x, -sent.y);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cfma(tot, H[u], R[u]);
+    stage.push(tot, c.s, lane, acc_out);
+    if (c.t_lo < len) stage.push(sent, c.s + 1, lane, acc_out);
   }
-  flush(acc_out, s, acc, lane);
-  flush(acc_out, s + 1, nxt, lane);
+  stage.drain(lane, acc_out);
+}
+
+// ---- TMA variant ---------------------------------------------------------------------------------
+// Same arithmetic, different data movement: every warp owns a contiguous, 2 KB-aligned segment of
+// the call and streams it through a private shared-memory ring of kTmaTiles x 2 KB tiles filled by
+// 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) that complete on per-tile mbarriers.  Bytes in
+// flight no longer cost registers: 3 CTAs x 8 warps x 3 tiles x 2 KB = 144 KB per SM are outstanding
+// while the warps compute from shared memory.  No cross-warp synchronisation after the prologue.
+constexpr int kTmaTile = 256;                   // samples per tile (2 KB)
+constexpr int kTmaTiles = 4;                    // ring depth per warp
+constexpr int kTmaRing = kTmaTile * kTmaTiles;  // samples per ring
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+__global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_tma_kernel(const IqbbFoldArgs a) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ float2 sA[128];
+  __shared__ float2 sH[256];
+  __shared__ __align__(8) unsigned long long bars[kFoldWarps][kTmaTiles];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (uint32_t k = blockIdx.x * blockDim.x + tid; k < a.zero_next; k += gridDim.x * blockDim.x)
+    ((float2 *)a.acc_next)[k] = make_float2(0.f, 0.f);
+  if (tid < 128) sA[tid] = a.tab_a[tid];
+  sH[tid] = a.tab_u[(size_t)tid * a.taps_len];
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < kTmaTiles; ++t) mbar_init(smem_u32(&bars[warp][t]), 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint64_t seg_lo64 = ((uint64_t)blockIdx.x * kFoldWarps + warp) * a.seg;
+  if (seg_lo64 >= a.n) return;
+  const uint32_t S_lo = (uint32_t)seg_lo64;
+  const uint32_t S_hi = (uint32_t)min((uint64_t)a.n, seg_lo64 + a.seg);
+  const float2 *__restrict__ x = (const float2 *)a.x;
+  float2 *ring = (float2 *)dyn_smem + (size_t)warp * kTmaRing;
+  const uint32_t ring_u32 = smem_u32(ring), bar_u32 = smem_u32(&bars[warp][0]);
+  const uint32_t n_tiles = (S_hi - S_lo + kTmaTile - 1) / kTmaTile;
+
+  // producer side (lane 0): tile t -> ring slot t % kTmaTiles
+  auto issue = [&](uint32_t t) {
+    const uint32_t start = S_lo + t * kTmaTile;
+    const uint32_t cnt = min((uint32_t)kTmaTile, S_hi - start);
+    const uint32_t bytes16 = (cnt * 8u) & ~15u;
+    const uint32_t slot = t % kTmaTiles;
+    mbar_expect_tx(bar_u32 + slot * 8, bytes16);
+    if (bytes16) tma_load_1d(ring_u32 + slot * (kTmaTile * 8), x + start, bytes16, bar_u32 + slot * 8);
+    if (cnt & 1u) ring[slot * kTmaTile + cnt - 1] = x[start + cnt - 1];     // odd tail of the call
+  };
+  if (lane == 0) {
+    for (uint32_t t = 0; t < min(n_tiles, (uint32_t)kTmaTiles); ++t) issue(t);
+  }
+  __syncwarp();
+  uint32_t landed = 0;      // tiles [0, landed) are known to be in shared memory
+  uint32_t issued = min(n_tiles, (uint32_t)kTmaTiles);
+
+  float *acc_out = (float *)a.acc_cur;
+  const int L1 = (int)a.taps_len - 1;
+  const int64_t win_off = (int64_t)a.first - (int64_t)a.r0;
+  const uint32_t inc32 = (32u * a.inc) & 0x7fffu, inc256 = (256u * a.inc) & 0x7fffu;
+
+  float2 base = make_float2(0.f, 0.f);
+  uint32_t base_slot = 0;
+  uint32_t s = (uint32_t)(((uint64_t)a.r0 + S_lo - ((a.first && S_lo > 0) ? 1u : 0u)) / a.ss);
+  for (uint32_t pos = S_lo; pos < S_hi; ++s) {
+    const int64_t full_end = (int64_t)((uint64_t)(s + 1) * a.ss) + win_off;
+    const uint32_t c_lo = pos;
+    const uint32_t c_hi = (uint32_t)min(full_end, (int64_t)S_hi);
+    const uint32_t len = c_hi - c_lo;
+    const int64_t t_lo64 = full_end - L1 - (int64_t)c_lo;
+    const uint32_t t_lo = t_lo64 < 0 ? 0u : (t_lo64 > (int64_t)len ? len : (uint32_t)t_lo64);
+    const uint32_t end_rel = (uint32_t)(full_end - (int64_t)c_lo);
+    pos = c_hi;
+
+    if (base_slot != s) { flush(acc_out, base_slot, base, lane); base = make_float2(0.f, 0.f); }
+    uint32_t ph = (a.phase0 + (c_lo + (uint32_t)lane) * a.inc) & 0x7fffu;
+    float2 H[8], R[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { H[u] = sH[(ph + u * inc32) & 255u]; R[u] = make_float2(0.f, 0.f); }
+    float2 sent = make_float2(0.f, 0.f);
+    uint32_t pb = 0; float2 Ab = make_float2(0.f, 0.f);
+    const float2 *__restrict__ urow = a.tab_u;
+    if (t_lo < len) {
+      pb = (a.phase0 + (uint32_t)full_end * a.inc) & 0x7fffu;
+      Ab = sA[pb >> 8];
+      urow = a.tab_u + (size_t)(pb & 255u) * a.taps_len;
+    }
+    const uint32_t roff = c_lo - S_lo + lane;             // segment-relative index of this lane's sample in step 0
+
+    for (uint32_t k = 0; k < len; k += 256, ph = (ph + inc256) & 0x7fffu) {
+      // tiles needed by this batch: up to the one holding its last sample
+      const uint32_t last = min(k + 256u, len) - 1u + (c_lo - S_lo);
+      const uint32_t need = last / kTmaTile + 1;
+      while (landed < need) { mbar_wait(bar_u32 + (landed % kTmaTiles) * 8, (landed / kTmaTiles) & 1u); ++landed; }
+      float2 xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t j = k + 32 * u + lane;
+        xv[u] = j < len ? ring[(roff + k + 32 * u) & (kTmaRing - 1)] : make_float2(0.f, 0.f);
+      }
+      if (k + 256 <= t_lo) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t js = k + 32 * u;
+          if (js >= len) break;
+          cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
+          if (js + 32 > t_lo) {
+            const uint32_t j = js + lane;
+            if (j >= t_lo && j < len) cfma(sent, cmul(Ab, __ldg(urow + (end_rel - j))), xv[u]);
+          }
+        }
+      }
+      // tiles that lie entirely before the next sample to be read are free: refill them
+      const uint32_t next_rel = min(k + 256u, len) + (c_lo - S_lo);
+      const uint32_t free_upto = next_rel / kTmaTile;       // tiles [0, free_upto) fully consumed
+      __syncwarp();
+      if (lane == 0) {
+        while (issued < n_tiles && issued < free_upto + kTmaTiles) { issue(issued); ++issued; }
+      } else {
+        const uint32_t cap = min(n_tiles, free_upto + (uint32_t)kTmaTiles);
+        if (issued < cap) issued = cap;
+      }
+      __syncwarp();
+    }
+    float2 tot = make_float2(base.x - sent.x, base.y - sent.y);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cfma(tot, H[u], R[u]);
+    flush(acc_out, s, tot, lane);
+    base = sent; base_slot = s + 1;
+  }
+  flush(acc_out, base_slot, base, lane);
 }
 
 }  // namespace
 
-int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st) {
-  if (a.n == 0) return SDRG_OK;
-  const uint64_t per_block = (uint64_t)a.seg * kFoldWarps;
-  const unsigned grid = (unsigned)((a.n + per_block - 1) / per_block);
-  iqbb_fold_f32_kernel<<<grid, kFoldThreads, 0, st>>>(a);
+// Grids are sized to the machine: 148 SMs x 3 resident CTAs of 8 warps.
+static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
+  // slots touched by this call: slot of the last sample + 1
+  const uint64_t q_last = (uint64_t)a.r0 + (a.n - 1) - ((a.first && a.n > 1) ? 1 : 0);
+  const uint64_t n_slots = q_last / a.ss + 1;
+  a.part = 8192;
+  a.cpw = (uint32_t)(((uint64_t)a.ss + 1 + a.part - 1) / a.part);
+  const uint64_t n_chunks = n_slots * a.cpw;
+  if (n_chunks > 0xffffffffull) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand<float>: too many windows in one call");
+  a.n_chunks = (uint32_t)n_chunks;
+  a.chunks_per_warp = 0;
+  static int resident = 0;     // CTAs that fit the device at once: SMs x occupancy
+  const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
+  if (!resident) {
+    SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    SDRG_CUDA(cudaGetDevice(&dev));
+    SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_f32_kernel, kFoldThreads, smem));
+    resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const uint64_t want = (n_chunks + kFoldWarps - 1) / kFoldWarps;
+  const unsigned grid = (unsigned)(want < (uint64_t)resident ? want : (uint64_t)resident);
+  iqbb_fold_f32_kernel<<<grid, kFoldThreads, smem, st>>>(a);
   SDRG_CHECK_LAUNCH("iqbb_fold_f32_kernel");
   return SDRG_OK;
+}
+
+static int launch_fold_tma(IqbbFoldArgs a, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = (size_t)kFoldWarps * kTmaRing * sizeof(float2);
+  if (!attr_set) {
+    SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  // one contiguous 2 KB-aligned segment per warp; ~2 waves of 148 x 3 CTAs
+  const uint64_t target_warps = 148ull * 3 * kFoldWarps * 2;
+  uint64_t seg = (a.n + target_warps - 1) / target_warps;
+  seg = ((seg + kTmaTile - 1) / kTmaTile) * kTmaTile;
+  if (seg < (uint64_t)kTmaTile) seg = kTmaTile;
+  a.seg = (uint32_t)seg;
+  const uint64_t per_block = seg * kFoldWarps;
+  const unsigned grid = (unsigned)((a.n + per_block - 1) / per_block);
+  iqbb_fold_f32_tma_kernel<<<grid, kFoldThreads, smem, st>>>(a);
+  SDRG_CHECK_LAUNCH("iqbb_fold_f32_tma_kernel");
+  return SDRG_OK;
+}
+
+int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st) {
+  if (a.n == 0) return SDRG_OK;
+  // bulk async copies need 16-byte aligned global addresses; otherwise use the LDG variant
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0;
+  static const int env_variant = [] { const char *e = getenv("SDRG_FOLD_VARIANT"); return e ? atoi(e) : 0; }();
+  const int variant = a.variant ? (int)a.variant : env_variant;      // 2 = TMA staging (experimental)
+  return (aligned && variant == 2) ? launch_fold_tma(a, st) : launch_fold_ldg(a, st);
 }
 
 }  // namespace sdrg

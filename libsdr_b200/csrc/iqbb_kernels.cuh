@@ -44,7 +44,13 @@ struct IqbbFoldArgs {
   uint32_t      r0, first;
   uint32_t      phase0, inc;
   uint32_t      zero_next;
-  uint32_t      seg;        // samples per warp segment (multiple of 32)
+  // work decomposition, filled in by launch_iqbb_fold()
+  uint32_t      part;       // a window longer than this is cut into pieces (chunks)
+  uint32_t      cpw;        // chunks per window
+  uint32_t      n_chunks;   // windows touched by this call x cpw
+  uint32_t      chunks_per_warp;
+  uint32_t      seg;        // TMA variant: samples per warp segment (multiple of 256)
+  uint32_t      variant;    // 0/1 LDG loads (default), 2 TMA bulk-copy staging (needs 16-byte aligned input)
 };
 
 // finalize (+ optional demodulation) of the completed windows of one call

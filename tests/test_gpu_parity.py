@@ -253,7 +253,7 @@ def _float_case(cfg, x, bs, demod=DEMOD_FM, path=0):
 PATHS = [(1, "direct"), (2, "folded")]
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["direct", "folded"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["direct", "folded", "folded-tma"])
 def test_c2_float_chain(path):
     cfg = dict(synth.C2)
     x = synth.c2_input(2 << 20)
@@ -267,21 +267,25 @@ def test_float_small_configs(demod, path):
     cfg = dict(scalar="f32", Fs=2.4e6, Fc=-100e3, Ff=-100e3, width=30e3, order=21, sub_sample=1, oFs=48000.0)
     x = synth.iq_f32(200000, 2.4e6, [(0.5, -103e3, 0.0), (0.2, 500e3, 1.0)], 0.01, 3)
     _float_case(cfg, x, 50000, demod, path)          # ss=50, negative shift
-    cfg.update(Fc=0.0, Ff=0.0)
-    _float_case(cfg, x, 50000, demod, path)          # lut_inc == 0: mixer bypassed
+    cfg.update(Fc=0.0, Ff=0.0, width=200e3)
+    x0 = synth.iq_f32(200000, 2.4e6, [(0.5, 3e3, 0.0), (0.2, 500e3, 1.0)], 0.01, 4)
+    _float_case(cfg, x0, 50000, demod, path)         # lut_inc == 0: mixer bypassed
     if path == 1:
         cfg.update(Fc=77e3, Ff=60e3, sub_sample=7, oFs=0.0, order=33)   # ss < order-1: direct only
         _float_case(cfg, x, 40000, demod, path)
 
 
-@pytest.mark.parametrize("ss,order", [(32, 33), (63, 64), (64, 64), (100, 2), (416, 1), (5000, 64), (300000, 128)])
-def test_float_folded_geometry(ss, order):
+@pytest.mark.parametrize("ss,order", [(32, 33), (63, 64), (64, 64), (100, 2), (416, 1), (417, 64), (5000, 64), (8191, 64), (8192, 64), (8193, 64), (300000, 128)])
+@pytest.mark.parametrize("path", [2, 3], ids=["folded", "folded-tma"])
+def test_float_folded_geometry(ss, order, path):
     """Folded kernel across window/segment geometries (window << segment, window >> segment,
     ss == order-1, order 1), ragged multi-call streams."""
-    cfg = dict(scalar="f32", Fs=20e6, Fc=1.23e6, Ff=1.2e6, width=200e3, order=order, sub_sample=ss, oFs=0.0)
+    # Fc = Fs/16 is exactly representable by the NCO (inc = 2048): the 1.25 MHz tone lands on DC and
+    # survives even the longest boxcar, so the relative error is well conditioned
+    cfg = dict(scalar="f32", Fs=20e6, Fc=1.25e6, Ff=1.2e6, width=200e3, order=order, sub_sample=ss, oFs=0.0)
     n = 700000
-    x = synth.iq_f32(n, 20e6, [(0.5, 1.25e6, 0.0), (0.3, -4e6, 1.0)], 0.02, 11)
-    g, o = gpu_bb(cfg, bs=n, float_path=2), orc_bb(cfg, bs=n)
+    x = synth.iq_f32(n, 20e6, [(0.5, 1.25e6, 0.3), (0.3, -4e6, 1.0)], 0.02, 11)
+    g, o = gpu_bb(cfg, bs=n, float_path=path), orc_bb(cfg, bs=n)
     cuts = [0, 1, 31, 32, 33, 2047, 2048, 2049, 100000, 100001, 400000, n]
     ys, os_ = [], []
     for s, e in zip(cuts[:-1], cuts[1:]):
@@ -290,6 +294,24 @@ def test_float_folded_geometry(ss, order):
     y, ob = np.concatenate(ys), np.concatenate(os_)
     if ob.shape[0]:
         e = rel_rms(y.astype(np.float64).view(np.complex128), ob.astype(np.float64).view(np.complex128))
+        assert e < FLOAT_TOL, e
+
+
+def test_float_folded_misaligned_device_input():
+    """An 8-byte (not 16-byte) aligned device pointer takes the LDG variant of the folded kernel;
+    the 16-byte aligned one the TMA variant.  Both must agree with the oracle."""
+    import torch
+    cfg = dict(synth.C2)
+    n = 300001
+    x = synth.c2_input(n + 1)
+    xd = torch.from_numpy(x).cuda()
+    o = orc_bb(cfg, bs=n)
+    ob = o.process(x[1:])
+    for view in (xd[1:], xd[1:].clone()):
+        g = gpu_bb(cfg, bs=n, float_path=2)
+        y = g.process(view)
+        torch.cuda.synchronize()
+        e = rel_rms(y.cpu().numpy().astype(np.float64).view(np.complex128), ob.astype(np.float64).view(np.complex128))
         assert e < FLOAT_TOL, e
 
 
