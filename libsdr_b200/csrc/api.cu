@@ -337,6 +337,12 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   a.phase0 = h->phase0; a.inc = (uint32_t)(h->d.lut_inc & 0x7fffu); a.nco = h->d.lut_inc != 0 ? 1u : 0u;
   a.neg = h->d.negative ? 1u : 0u;
   a.zero_next = h->acc_dirty[q];
+  IqbbFinalizeArgs f{};
+  f.acc_cur = h->d_acc[p]; f.acc_next = h->d_acc[q];
+  f.bb_out = d_bb; f.audio_out = d_audio;
+  f.fm_last_in = fm_last_in; f.fm_last_out = fm_last_out;
+  f.n_out = (uint32_t)adv.n_out; f.ss = a.ss; f.demod = (uint32_t)demod; f.e0 = adv.e0;
+  f.seg = seg; f.in_place = (uint32_t)in_place;
   if (h->fold) {
     IqbbFoldArgs fa{};
     fa.x = d_in; fa.acc_cur = a.acc_cur; fa.acc_next = a.acc_next;
@@ -351,12 +357,6 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
     rc = launch_iqbb_accum(h->d.scalar, a, st);
   }
   if (rc) return rc;
-  IqbbFinalizeArgs f{};
-  f.acc_cur = h->d_acc[p]; f.acc_next = h->d_acc[q];
-  f.bb_out = d_bb; f.audio_out = d_audio;
-  f.fm_last_in = fm_last_in; f.fm_last_out = fm_last_out;
-  f.n_out = (uint32_t)adv.n_out; f.ss = a.ss; f.demod = (uint32_t)demod; f.e0 = adv.e0;
-  f.seg = seg; f.in_place = (uint32_t)in_place;
   {
     ProfScope ps(SDRG_KERNEL_IQBB_FINALIZE, st);
     rc = launch_iqbb_finalize(h->d.scalar, f, st);

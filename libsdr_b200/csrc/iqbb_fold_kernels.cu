@@ -65,7 +65,7 @@ __device__ __forceinline__ void flush(float *acc, uint32_t slot, float2 v, int l
 // this warp finished; once 32 rows are full lane l sums row l (one LDS.64 per element, rows padded
 // to 33 to stay conflict free) and issues the RED.ADDs for its window.  This replaces a 5-step
 // shuffle reduction per component per window by ~3 instructions per window.
-constexpr int kStageRows = 32, kStagePitch = 33;
+constexpr int kStageRows = 16, kStagePitch = 33;
 
 struct WarpStage {
   float2 *rows;      // [kStageRows][kStagePitch]
@@ -82,7 +82,7 @@ struct WarpStage {
       float sr = 0.f, si = 0.f;
       const float2 *r = rows + lane * kStagePitch;
 #pragma unroll 8
-      for (int i = 0; i < 32; ++i) { const float2 v = r[i]; sr += v.x; si += v.y; }
+      for (int i = 0; i < 32; ++i) { const float2 v = r[i]; sr += v.x; si += v.y; }   // the 32 lane partials of row `lane`
       if (sr != 0.f || si != 0.f) { atomicAdd(acc_out + 2 * (size_t)my_slot, sr); atomicAdd(acc_out + 2 * (size_t)my_slot + 1, si); }
     }
     __syncwarp();
@@ -108,7 +108,7 @@ __device__ __forceinline__ bool chunk_of(const IqbbFoldArgs &a, uint32_t id, int
 // Persistent grid (one CTA per resident slot); chunk ids are dealt round-robin to the warps of the
 // whole grid, so that at any moment the running warps read ONE compact, linearly advancing region
 // of the input (DRAM row locality, like a grid-stride loop) instead of thousands of separate fronts.
-__global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_kernel(const IqbbFoldArgs a) {
+__global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const IqbbFoldArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ float2 sA[128];
   __shared__ float2 sH[256];
@@ -123,8 +123,6 @@ __global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_kernel(const Iq
 
   const uint32_t total_warps = gridDim.x * kFoldWarps;
   const uint32_t wg = warp * gridDim.x + blockIdx.x;        // neighbouring CTAs take neighbouring chunks
-  if (wg >= a.n_chunks) return;
-
   const float2 *__restrict__ x = (const float2 *)a.x;
   float *acc_out = (float *)a.acc_cur;
   WarpStage stage{(float2 *)dyn_smem + (size_t)warp * kStageRows * kStagePitch, 0u, 0u};
@@ -141,9 +139,10 @@ __global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_kernel(const Iq
     if (!chunk_of(a, id, win_off, L1, c)) continue;
     const int len = c.len;
     uint32_t ph = (a.phase0 + (uint32_t)(c.c_lo + lane) * a.inc) & 0x7fffu;         // this lane's phase in step 0
-    float2 H[8], R[8];
+    const uint32_t r0 = ph & 255u;        // low phase byte in step 0; step u has (r0 + u*inc32) & 255 in every batch
+    float2 R[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { H[u] = sH[(ph + u * inc32) & 255u]; R[u] = make_float2(0.f, 0.f); }
+    for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
     const float2 *__restrict__ xc = x + c.c_lo + lane;
 
     // every sample: R_u += A(a_p) x[p]   (its full weight G = H_u A)
@@ -180,11 +179,12 @@ __global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_kernel(const Iq
     }
     float2 tot = make_float2(-sent.x, -sent.y);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) cfma(tot, H[u], R[u]);
+    for (int u = 0; u < 8; ++u) cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);   // H_u = U(r_u, 0)
     stage.push(tot, c.s, lane, acc_out);
     if (c.t_lo < len) stage.push(sent, c.s + 1, lane, acc_out);
   }
   stage.drain(lane, acc_out);
+
 }
 
 // ---- TMA variant ---------------------------------------------------------------------------------
