@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
 
   for (uint32_t id = wg; id < a.n_chunks; id += total_warps) {
     Chunk c;
-    if (lane == 0 && id + total_warps < a.n_chunks) {       // next chunk of this warp -> L2, one instruction
+    if (lane == 0 && a.pf_dist && id + a.pf_dist * total_warps < a.n_chunks) {   // a later chunk of this warp -> L2, one instruction
       Chunk nx;
-      if (chunk_of(a, id + total_warps, win_off, L1, nx)) prefetch_l2(x + nx.c_lo, x + nx.c_lo + nx.len);
+      if (chunk_of(a, id + a.pf_dist * total_warps, win_off, L1, nx)) prefetch_l2(x + nx.c_lo, x + nx.c_lo + nx.len);
     }
     if (!chunk_of(a, id, win_off, L1, c)) continue;
     const int len = c.len;
@@ -154,6 +154,21 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
 #pragma unroll
       for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
     }
+    // The last L-1 samples of the window also owe T_e x to the next window.  Their loads (a re-read
+    // of x, L2 resident, and the U(r_b, e) row) are issued together with the ragged batch so that
+    // the window costs two memory round trips, not three.
+    float2 sent = make_float2(0.f, 0.f);
+    const bool has_tail = c.t_lo < len;
+    const int jt = c.t_lo + lane;                                   // this lane's first tail sample
+    float2 Ab = make_float2(0.f, 0.f), xt0 = Ab, xt1 = Ab, ut0 = Ab, ut1 = Ab;
+    const float2 *__restrict__ ue = a.tab_u;
+    if (has_tail) {
+      const uint32_t pb = (a.phase0 + (uint32_t)c.full_end * a.inc) & 0x7fffu;
+      Ab = sA[pb >> 8];
+      ue = a.tab_u + (size_t)(pb & 255u) * a.taps_len + (c.full_end - c.c_lo - lane);   // U(r_b, e), e = end - j
+      if (jt < len) { xt0 = __ldg(xc + (jt - lane)); ut0 = __ldg(ue - (jt - lane)); }
+      if (jt + 32 < len) { xt1 = __ldg(xc + (jt + 32 - lane)); ut1 = __ldg(ue - (jt + 32 - lane)); }
+    }
     if (k < len) {                        // ragged last batch
       const int rem = len - k;
       float2 xv[8];
@@ -168,13 +183,10 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
         cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
       }
     }
-    // the last L-1 samples of the window also owe T_e x to the next window (re-read, L1/L2 resident)
-    float2 sent = make_float2(0.f, 0.f);
-    if (c.t_lo < len) {
-      const uint32_t pb = (a.phase0 + (uint32_t)c.full_end * a.inc) & 0x7fffu;
-      const float2 Ab = sA[pb >> 8];
-      const float2 *__restrict__ ue = a.tab_u + (size_t)(pb & 255u) * a.taps_len + (c.full_end - c.c_lo - lane);  // U(r_b, e), e = end - j
-      for (int j = c.t_lo + lane; j < len; j += 32)
+    if (has_tail) {
+      cfma(sent, cmul(Ab, ut0), xt0);     // zero when this lane has no such sample
+      cfma(sent, cmul(Ab, ut1), xt1);
+      for (int j = jt + 64; j < len; j += 32)       // L > 65 only
         cfma(sent, cmul(Ab, __ldg(ue - (j - lane))), __ldg(xc + (j - lane)));
     }
     float2 tot = make_float2(-sent.x, -sent.y);
@@ -353,6 +365,8 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   if (n_chunks > 0xffffffffull) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand<float>: too many windows in one call");
   a.n_chunks = (uint32_t)n_chunks;
   a.chunks_per_warp = 0;
+  static const int pf = [] { const char *e = getenv("SDRG_FOLD_PF"); return e ? atoi(e) : 0; }();   // measured: no gain with round-robin chunks
+  a.pf_dist = (uint32_t)pf;
   static int resident = 0;     // CTAs that fit the device at once: SMs x occupancy
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
   if (!resident) {

@@ -49,6 +49,7 @@ struct IqbbFoldArgs {
   uint32_t      cpw;        // chunks per window
   uint32_t      n_chunks;   // windows touched by this call x cpw
   uint32_t      chunks_per_warp;
+  uint32_t      pf_dist;    // L2 prefetch distance in chunks of the same warp (0 = off)
   uint32_t      seg;        // TMA variant: samples per warp segment (multiple of 256)
   uint32_t      variant;    // 0/1 LDG loads (default), 2 TMA bulk-copy staging (needs 16-byte aligned input)
 };
