@@ -48,7 +48,7 @@ def config_block(c, n_gpus, extra=None):
            "scalar": "cf32", "order": c["order"], "sample_rate": c["Fs"], "output_rate": c["oFs"],
            "buffer_size": c["buffer_size"], "buffers_per_step": c["n_buffers"],
            "samples_per_step_per_gpu": c["buffer_size"] * c["n_buffers"],
-           "l2_policy": "inputs larger than L2 (512 MiB per step per GPU)",
+           "l2_policy": "inputs larger than L2 (%d MiB per step per GPU)" % (c["buffer_size"] * c["n_buffers"] * 8 >> 20),
            "input": "3 tones + uniform noise (synth.c2_input), a 4 Mi-sample segment tiled to the batch",
            "parallelism": "independent streams per GPU (replicas), NCCL all_gather of audio" if n_gpus > 1 else "single GPU"}
     if extra:
@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--buffers", type=int, default=0, help="buffers per step (default: the workload's n_buffers)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -203,6 +204,8 @@ def main():
     K = max(args.steps, 1)
 
     c = workload()
+    if args.buffers:
+        c["n_buffers"] = args.buffers
     bs, nb = c["buffer_size"], c["n_buffers"]
     n_step = bs * nb
     x_host = torch.from_numpy(make_input(c)).pin_memory()

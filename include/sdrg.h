@@ -69,6 +69,19 @@ int sdrg_buffer_mark_device_valid(const void *host_ptr, size_t bytes, void *stre
 int sdrg_buffer_device_valid(const void *host_ptr, size_t bytes, int *valid);
 int sdrg_buffer_invalidate_device(const void *host_ptr);                     /* host becomes authoritative again */
 int sdrg_buffer_sync_to_host(const void *host_ptr, size_t bytes);            /* no-op unless the range is device-valid and unsynced */
+/* Device address of [host_ptr, +bytes) with the data present: a device-valid range is used as is,
+ * anything else is copied up first (async on `stream`; pinned, so truly asynchronous).  For memory
+ * that is NOT a managed buffer, *dev_ptr is set to NULL and the caller stages it itself. */
+int sdrg_buffer_to_device(const void *host_ptr, size_t bytes, void *stream, void **dev_ptr);
+
+/* The library's compute stream (one per device, non-blocking): nodes that chain on the device
+ * launch on it so that producer -> consumer order needs no events. */
+int sdrg_stream_default(void **stream);
+int sdrg_stream_synchronize(void *stream);
+/* device scratch of at least `bytes`, private to the calling thread, valid until its next call */
+int sdrg_scratch(size_t bytes, void **dev_ptr);
+int sdrg_memcpy_h2d_async(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int sdrg_memcpy_d2h_async(void *h_dst, const void *d_src, size_t bytes, void *stream);
 
 /* ---- IQBaseBand<Scalar> (src/baseband.hh:21-297; FreqShiftBase src/freqshift.hh:13-107) -------
  * scalar: SDRG_T_S8, SDRG_T_S16 or SDRG_T_F32.  Integer paths are bit-exact w.r.t. the reference;
@@ -125,7 +138,9 @@ enum { SDRG_DEMOD_NONE = 0, SDRG_DEMOD_FM = 1, SDRG_DEMOD_AM = 2, SDRG_DEMOD_USB
 /* FMDemod<iScalar,oScalar> (demod.hh:172-266, fast_atan2 src/math.hh:9-40).
  * in_scalar S8/S16 -> int16 output; F32 -> float output (defined in DESIGN.md).
  * Element 0 of every processed buffer is skipped exactly like the reference: with in_place != 0 it
- * shows the bytes of the input that alias it, otherwise the output element is left untouched. */
+ * shows the bytes of the input that alias it, otherwise the output element is left untouched.
+ * The _dev variants accept d_out == d_in (true in-place use, demod.hh:233-234): the result is then
+ * formed in scratch memory and copied over the input in stream order. */
 typedef struct sdrg_fmdemod sdrg_fmdemod;
 int sdrg_fmdemod_create(int in_scalar, sdrg_fmdemod **h);
 int sdrg_fmdemod_destroy(sdrg_fmdemod *h);

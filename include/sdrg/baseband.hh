@@ -1,0 +1,97 @@
+// sdrg/baseband.hh -- IQBaseBand<Scalar> as a GPU node behind libsdr's node interface.
+// Same constructors, setters, config()/process() meaning and error behaviour as
+// src/baseband.hh:21-297; the work is done by libsdrg (sdrg_iqbb_*).  Scalar: int8_t, int16_t
+// (bit-exact w.r.t. the reference) or float (defined in DESIGN.md).
+#ifndef SDRG_BASEBAND_HH
+#define SDRG_BASEBAND_HH
+
+#include "gpu.hh"
+#include "logger.hh"
+#include "node.hh"
+#include "traits.hh"
+
+namespace sdr {
+
+template <class Scalar>
+class IQBaseBand : public Sink< std::complex<Scalar> >, public Source {
+public:
+  typedef std::complex<Scalar> CScalar;
+
+  /** Filter centre frequency equals the shift frequency Fc (src/baseband.hh:35). */
+  IQBaseBand(double Fc, double width, size_t order, size_t sub_sample, double oFs = 0.0) : _h(0) {
+    gpu::check(sdrg_iqbb_create(Traits<Scalar>::scalarId, Fc, Fc, width, order, sub_sample, oFs, &_h));
+  }
+  IQBaseBand(double Fc, double Ff, double width, size_t order, size_t sub_sample, double oFs = 0.0) : _h(0) {
+    gpu::check(sdrg_iqbb_create(Traits<Scalar>::scalarId, Fc, Ff, width, order, sub_sample, oFs, &_h));
+  }
+  virtual ~IQBaseBand() { sdrg_iqbb_destroy(_h); _buffer.unref(); }
+
+  size_t order() const { return info().order; }
+  void setOrder(size_t o) { gpu::check(sdrg_iqbb_set_order(_h, o)); }
+  void setCenterFrequency(double Fc) { gpu::check(sdrg_iqbb_set_center_frequency(_h, Fc)); }
+  void setFilterFrequency(double Ff) { gpu::check(sdrg_iqbb_set_filter_frequency(_h, Ff)); }
+  void setFilterWidth(double width) { gpu::check(sdrg_iqbb_set_filter_width(_h, width)); }
+  size_t subSample() const { return info().sub_sample; }
+  void setSubsample(size_t ss) { gpu::check(sdrg_iqbb_set_subsample(_h, ss)); republish(); }
+  void setOutputSampleRate(double Fs) { gpu::check(sdrg_iqbb_set_output_sample_rate(_h, Fs)); republish(); }
+
+  virtual bool acceptsDeviceBuffers() const { return true; }
+
+  virtual void config(const Config &src_cfg) {
+    const sdrg_config in = src_cfg.c();
+    sdrg_config out;
+    gpu::check(sdrg_iqbb_configure(_h, &in, &out));   // throws ConfigError on a type mismatch
+    if (SDRG_T_UNDEFINED == out.type) return;         // incomplete config: ignored (baseband.hh:118)
+    _src = src_cfg; _out = out;
+    _buffer.unref();
+    _buffer = Buffer<CScalar>(out.buffer_size);
+    LogMessage msg(LOG_DEBUG);
+    msg << "Configured IQBaseBand node (B200):" << std::endl
+        << " type " << src_cfg.type() << std::endl << " sample-rate " << src_cfg.sampleRate() << "Hz" << std::endl
+        << " in buffer size " << src_cfg.bufferSize() << std::endl << " sub-sample by " << info().sub_sample << std::endl
+        << " out buffer size " << out.buffer_size;
+    Logger::get().log(msg);
+    this->setConfig(Config::from(out));
+  }
+
+  virtual void process(const Buffer<CScalar> &buffer, bool allow_overwrite) {
+    if (allow_overwrite) run(buffer, buffer);
+    else if (_buffer.isUnused()) run(buffer, _buffer);
+    // else: output buffer still in use -> the input is dropped, like the reference (baseband.hh:141-150)
+  }
+
+protected:
+  sdrg_iqbb_info info() const { sdrg_iqbb_info i; gpu::check(sdrg_iqbb_get_info(_h, &i, 0, 0)); return i; }
+  void republish() {    // the rate setters reconfigure and publish a new output config (baseband.hh:156-194)
+    if (!_src.hasType() || !_src.hasSampleRate() || !_src.hasBufferSize()) return;
+    config(_src);
+  }
+  void run(const Buffer<CScalar> &in, const Buffer<CScalar> &out) {
+    void *st = gpu::stream();
+    const void *d_in = gpu::deviceInput(in, st);
+    size_t n_out = 0;
+    gpu::check(sdrg_iqbb_outputs_for(_h, in.size(), &n_out));
+    if (n_out > out.size()) { RuntimeError err; err << "IQBaseBand: output buffer too small"; throw err; }
+    void *d_out = gpu::deviceOutput(out);
+    const bool staged = (0 == d_out);           // `out` wraps foreign memory: scratch + copy back
+    void *d_tmp = 0;
+    if (staged && n_out) { gpu::check(sdrg_buffer_alloc(n_out * sizeof(CScalar), &d_tmp)); d_out = gpu::deviceOutput(RawBuffer((char *)d_tmp, 0, 1)); }
+    // The finalize kernel writes the outputs only after the accumulate kernel has consumed every
+    // input sample (stream order), so `out` may alias `in` on the device as it does on the host.
+    gpu::check(sdrg_iqbb_process_dev(_h, d_in, in.size(), d_out, n_out, &n_out, st));
+    if (staged) {
+      if (n_out) { gpu::check(sdrg_memcpy_d2h_async(out.data(), d_out, n_out * sizeof(CScalar), st)); gpu::check(sdrg_stream_synchronize(st)); sdrg_buffer_free(d_tmp); }
+    } else if (n_out) {
+      gpu::publish(out, n_out * sizeof(CScalar), st);
+    }
+    this->send(out.head(n_out), true);
+  }
+
+  sdrg_iqbb *_h;
+  Config _src;
+  sdrg_config _out;
+  Buffer<CScalar> _buffer;
+};
+
+}  // namespace sdr
+#endif

@@ -63,6 +63,12 @@ SIGNATURES = {
     "sdrg_buffer_device_valid": [_V, _SZ, C.POINTER(C.c_int)],
     "sdrg_buffer_invalidate_device": [_V],
     "sdrg_buffer_sync_to_host": [_V, _SZ],
+    "sdrg_buffer_to_device": [_V, _SZ, _V, _PV],
+    "sdrg_stream_default": [_PV],
+    "sdrg_stream_synchronize": [_V],
+    "sdrg_scratch": [_SZ, _PV],
+    "sdrg_memcpy_h2d_async": [_V, _V, _SZ, _V],
+    "sdrg_memcpy_d2h_async": [_V, _V, _SZ, _V],
     "sdrg_iqbb_create": [_I, _D, _D, _D, _SZ, _SZ, _D, _PV],
     "sdrg_iqbb_destroy": [_V],
     "sdrg_iqbb_set_center_frequency": [_V, _D],

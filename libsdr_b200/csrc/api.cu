@@ -118,6 +118,7 @@ struct sdrg_iqbb {
 
 struct sdrg_fmdemod {
   int scalar = SDRG_T_S16, device = 0;
+  void *d_alias = nullptr; size_t alias_cap = 0;   // result staging for aliased (in-place) device calls
   void *d_last[2] = {nullptr, nullptr};
   int parity = 0;
   cudaStream_t stream = nullptr;
@@ -534,6 +535,68 @@ int sdrg_buffer_sync_to_host(const void *host_ptr, size_t bytes) {
   return SDRG_OK;
 }
 
+int sdrg_buffer_to_device(const void *host_ptr, size_t bytes, void *stream, void **dev_ptr) {
+  if (!dev_ptr) return set_error(SDRG_ERR_ARG, "null argument");
+  *dev_ptr = nullptr;
+  char *dev = nullptr; bool copy = true; int device = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    ManagedBuffer *b = find_buffer(host_ptr);
+    if (!b) return SDRG_OK;
+    const size_t lo = (const char *)host_ptr - b->host;
+    if (lo + bytes > b->bytes) return set_error(SDRG_ERR_ARG, "sdrg_buffer_to_device: range exceeds the buffer");
+    dev = b->dev + lo; device = b->device;
+    if (b->valid_hi > b->valid_lo && lo >= b->valid_lo && lo + bytes <= b->valid_hi) copy = false;
+    else { b->valid_lo = b->valid_hi = 0; b->host_synced = true; }     // the host copy is authoritative
+  }
+  if (copy && bytes) {
+    SDRG_CUDA(cudaSetDevice(device));
+    SDRG_CUDA(cudaMemcpyAsync(dev, host_ptr, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  }
+  *dev_ptr = dev;
+  return SDRG_OK;
+}
+
+static std::mutex g_stream_mu;
+static std::map<int, cudaStream_t> g_streams;
+int sdrg_stream_default(void **stream) {
+  if (!stream) return set_error(SDRG_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(g_stream_mu);
+  auto it = g_streams.find(g_device);
+  if (it == g_streams.end()) {
+    cudaStream_t s = nullptr;
+    SDRG_CUDA(cudaSetDevice(g_device));
+    SDRG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    it = g_streams.emplace(g_device, s).first;
+  }
+  *stream = (void *)it->second;
+  return SDRG_OK;
+}
+int sdrg_stream_synchronize(void *stream) { SDRG_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return SDRG_OK; }
+
+struct ThreadScratch { void *p = nullptr; size_t cap = 0; int device = -1; ~ThreadScratch() { if (p) cudaFree(p); } };
+static thread_local ThreadScratch g_scratch;
+int sdrg_scratch(size_t bytes, void **dev_ptr) {
+  if (!dev_ptr) return set_error(SDRG_ERR_ARG, "null argument");
+  if (g_scratch.device != g_device || g_scratch.cap < bytes) {
+    SDRG_CUDA(cudaSetDevice(g_device));
+    if (g_scratch.p) { SDRG_CUDA(cudaDeviceSynchronize()); cudaFree(g_scratch.p); g_scratch.p = nullptr; g_scratch.cap = 0; }
+    const size_t want = bytes < 65536 ? 65536 : bytes + bytes / 2;
+    SDRG_CUDA(cudaMalloc(&g_scratch.p, want));
+    g_scratch.cap = want; g_scratch.device = g_device;
+  }
+  *dev_ptr = g_scratch.p;
+  return SDRG_OK;
+}
+int sdrg_memcpy_h2d_async(void *d_dst, const void *h_src, size_t bytes, void *stream) {
+  if (bytes) SDRG_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return SDRG_OK;
+}
+int sdrg_memcpy_d2h_async(void *h_dst, const void *d_src, size_t bytes, void *stream) {
+  if (bytes) SDRG_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return SDRG_OK;
+}
+
 // ---- IQBaseBand ---------------------------------------------------------------------------------
 int sdrg_iqbb_create(int scalar, double Fc, double Ff, double width, size_t order, size_t sub_sample,
                      double oFs, sdrg_iqbb **out) {
@@ -791,7 +854,7 @@ int sdrg_fmdemod_destroy(sdrg_fmdemod *h) {
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   else cudaDeviceSynchronize();
-  free_dev(&h->d_last[0]); free_dev(&h->d_last[1]); free_dev(&h->d_in); free_dev(&h->d_out);
+  free_dev(&h->d_last[0]); free_dev(&h->d_last[1]); free_dev(&h->d_in); free_dev(&h->d_out); free_dev(&h->d_alias);
   delete h;
   return SDRG_OK;
 }
@@ -815,9 +878,16 @@ int sdrg_fmdemod_process_dev(sdrg_fmdemod *h, const void *d_in, size_t n, void *
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (n == 0) return SDRG_OK;                    // demod.hh:231
   SDRG_CUDA(cudaSetDevice(h->device));
-  if (d_in == d_out) return set_error(SDRG_ERR_ARG, "FMDemod: device input and output must not alias (pass in_place=1 for the in-place view semantics)");
-  int rc = launch_fmdemod(h->scalar, d_in, n, d_out, h->d_last[h->parity], h->d_last[h->parity ^ 1], in_place, (cudaStream_t)stream);
+  const size_t ob = audio_bytes(h->scalar, SDRG_DEMOD_FM);
+  void *dst = d_out;
+  if (d_in == d_out) {            // true in-place use: form the result aside, then copy it over the input
+    int rc = grow(&h->d_alias, &h->alias_cap, n * ob);
+    if (rc) return rc;
+    dst = h->d_alias; in_place = 1;
+  }
+  int rc = launch_fmdemod(h->scalar, d_in, n, dst, h->d_last[h->parity], h->d_last[h->parity ^ 1], in_place, (cudaStream_t)stream);
   if (rc) return rc;
+  if (dst != d_out) SDRG_CUDA(cudaMemcpyAsync(d_out, dst, n * ob, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   h->parity ^= 1;
   return SDRG_OK;
 }
@@ -860,11 +930,23 @@ int sdrg_amdemod_configure(int scalar, const sdrg_config *src, sdrg_config *out)
 int sdrg_usbdemod_configure(int scalar, const sdrg_config *src, sdrg_config *out) {
   return envelope_configure("USBDemod", scalar, src, out, false);    // demod.hh:140-141 sets 1
 }
+static int envelope_dev(bool usb, int scalar, const void *d_in, size_t n, void *d_out, void *stream) {
+  void *dst = d_out;
+  const size_t ob = scalar_bytes(scalar);
+  if (d_in == d_out && n) {       // in-place use (demod.hh:68, 145-147): result aside, then over the input
+    int rc = sdrg_scratch(n * ob, &dst);
+    if (rc) return rc;
+  }
+  int rc = usb ? launch_usbdemod(scalar, d_in, n, dst, (cudaStream_t)stream) : launch_amdemod(scalar, d_in, n, dst, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (dst != d_out) SDRG_CUDA(cudaMemcpyAsync(d_out, dst, n * ob, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SDRG_OK;
+}
 int sdrg_amdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream) {
-  return launch_amdemod(scalar, d_in, n, d_out, (cudaStream_t)stream);
+  return envelope_dev(false, scalar, d_in, n, d_out, stream);
 }
 int sdrg_usbdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream) {
-  return launch_usbdemod(scalar, d_in, n, d_out, (cudaStream_t)stream);
+  return envelope_dev(true, scalar, d_in, n, d_out, stream);
 }
 static int envelope_host(bool usb, int scalar, const void *in, size_t n, void *out) {
   if (n == 0) return SDRG_OK;
