@@ -171,6 +171,35 @@ int sdrg_rxchain_process_dev(sdrg_rxchain *h, const void *d_in, size_t buffer_si
                              void *stream);
 int sdrg_rxchain_process(sdrg_rxchain *h, const void *in, size_t buffer_size, size_t n_buffers,
                          void *bb, void *audio, size_t out_cap, size_t *n_out, size_t *counts);
+/* ---- FFTPlan<float> (src/fftplan.hh:11-34, src/fftplan_fftw3.hh:79-142; FFTW3 is replaced by a
+ *      hand-written shared-memory Stockham FFT).  Unnormalised c2c DFT, direction 0 = FORWARD
+ *      (exp(-i..)), 1 = BACKWARD.  Sizes: powers of two 2..8192; anything else is SDRG_ERR_CONFIG,
+ *      as is an empty buffer (fftplan_fftw3.hh:87-97).  `batch` transforms are contiguous. -------- */
+typedef struct sdrg_fft sdrg_fft;
+int sdrg_fft_create(size_t n, int direction, sdrg_fft **h);
+int sdrg_fft_destroy(sdrg_fft *h);
+int sdrg_fft_exec(sdrg_fft *h, const void *in, void *out, size_t batch);
+int sdrg_fft_exec_dev(sdrg_fft *h, const void *d_in, void *d_out, size_t batch, void *stream);
+
+/* ---- FilterNode<float> (src/filternode.hh:231-283): FilterSink (forward FFT of 2*block, shared) +
+ *      one FilterSource per added filter (spectrum multiply, backward FFT, overlap), and the
+ *      BufferNode that re-chunks arbitrary input sizes to `block` samples (src/buffernode.hh).
+ *      Complex float in, complex float out; block: powers of two 1..4096. ----------------------- */
+typedef struct sdrg_filter sdrg_filter;
+int sdrg_filter_create(size_t block_size, sdrg_filter **h);                      /* filternode.hh:236-246 */
+int sdrg_filter_destroy(sdrg_filter *h);
+int sdrg_filter_add(sdrg_filter *h, double fmin, double fmax, size_t *index);    /* addFilter, filternode.hh:262-270 */
+int sdrg_filter_set_freq(sdrg_filter *h, size_t index, double fmin, double fmax);/* FilterSource::setFreq, :128-130 */
+int sdrg_filter_count(const sdrg_filter *h, size_t *n);
+int sdrg_filter_configure(sdrg_filter *h, const sdrg_config *src, sdrg_config *out);   /* filternode.hh:56-79,133-160 */
+/* kern: 2*block complex floats (normalised spectrum), taps: block complex floats; either may be NULL */
+int sdrg_filter_get_design(const sdrg_filter *h, size_t index, void *kern_2n, void *taps_n);
+int sdrg_filter_outputs_for(const sdrg_filter *h, size_t n_in, size_t *n_out);
+/* filter f's output lands at out + f*out_stride (in samples); *n_out = samples produced per filter */
+int sdrg_filter_process(sdrg_filter *h, const void *in, size_t n_in, void *out, size_t out_stride, size_t *n_out);
+int sdrg_filter_process_dev(sdrg_filter *h, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
+                            size_t *n_out, void *stream);
+
 /* number of kernels the library has launched so far (all handles, this process) */
 int sdrg_kernel_launch_count(uint64_t *count);
 

@@ -100,6 +100,20 @@ SIGNATURES = {
     "sdrg_rxchain_reset": [_V],
     "sdrg_rxchain_process_dev": [_V, _V, _SZ, _SZ, _V, _V, _SZ, _PSZ, _PSZ, _V],
     "sdrg_rxchain_process": [_V, _V, _SZ, _SZ, _V, _V, _SZ, _PSZ, _PSZ],
+    "sdrg_fft_create": [_SZ, _I, _PV],
+    "sdrg_fft_destroy": [_V],
+    "sdrg_fft_exec": [_V, _V, _V, _SZ],
+    "sdrg_fft_exec_dev": [_V, _V, _V, _SZ, _V],
+    "sdrg_filter_create": [_SZ, _PV],
+    "sdrg_filter_destroy": [_V],
+    "sdrg_filter_add": [_V, _D, _D, _PSZ],
+    "sdrg_filter_set_freq": [_V, _SZ, _D, _D],
+    "sdrg_filter_count": [_V, _PSZ],
+    "sdrg_filter_configure": [_V, _PCFG, _PCFG],
+    "sdrg_filter_get_design": [_V, _SZ, _V, _V],
+    "sdrg_filter_outputs_for": [_V, _SZ, _PSZ],
+    "sdrg_filter_process": [_V, _V, _SZ, _V, _SZ, _PSZ],
+    "sdrg_filter_process_dev": [_V, _V, _SZ, _V, _SZ, _PSZ, _V],
     "sdrg_kernel_launch_count": [C.POINTER(C.c_uint64)],
     "sdrg_profile_enable": [_I],
     "sdrg_profile_read": [_I, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],

@@ -1,0 +1,182 @@
+// fft_kernels.cu -- shared-memory Stockham FFT and the fused FFT-convolution filter.
+//
+// Replaces, on the device:
+//   FFTPlan<float> / FFT::exec (src/fftplan.hh:11-34, src/fftplan_fftw3.hh:79-142; FFTW3 itself is
+//   an external, un-vendored dependency): unnormalised c2c DFT, FORWARD = exp(-i..), any power of
+//   two 2..8192, one CTA per transform, no cuFFT.
+//   FilterSink + FilterSource (src/filternode.hh:81-88,164-181): per block of N samples, a forward
+//   FFT of size 2N shared by all filters of the bank, then per filter a spectrum multiply, a
+//   backward FFT, 1/(2N) scaling and the overlap.
+// The overlap is evaluated as overlap-SAVE (each CTA transforms [previous block | current block]
+// and keeps the second half) instead of the reference's overlap-ADD: both compute the same causal
+// linear convolution y[n] = sum_j (h[j]/nrm) x[n-j], but overlap-save has no
+// dependency between consecutive blocks, so all blocks of a buffer run in parallel; the carried
+// state is the last N input samples instead of the last N output partials.
+//
+// Stockham autosort, decimation in time: at a stage with radix R and Ns = product of the radices
+// already applied, butterfly j (0 <= j < n/R) reads x[j + r n/R], multiplies by w^(r (j mod Ns))
+// with w = exp(-/+ 2 pi i /(Ns R)), applies the R-point DFT in registers and writes to
+// (j div Ns) Ns R + (j mod Ns) + r Ns.  Twiddles come from a table of n-th roots of unity computed
+// in double on the host.  Data ping-pongs between shared-memory buffers; one __syncthreads per stage.
+#include "fft_kernels.cuh"
+
+namespace sdrg {
+namespace {
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+template <bool INV> __device__ __forceinline__ void dft2(float2 &a, float2 &b) { const float2 t = a; a = caddf(t, b); b = csubf(t, b); }
+template <bool INV> __device__ __forceinline__ void dft4(float2 *v) {
+  dft2<INV>(v[0], v[2]); dft2<INV>(v[1], v[3]);
+  v[3] = rot90<INV>(v[3]);
+  dft2<INV>(v[0], v[1]); dft2<INV>(v[2], v[3]);
+  const float2 t = v[1]; v[1] = v[2]; v[2] = t;       // bit reversal: outputs 0,2,1,3 -> natural
+}
+template <bool INV> __device__ __forceinline__ void dft8(float2 *v) {
+  const float h = 0.70710678118654752440f;
+  dft2<INV>(v[0], v[4]); dft2<INV>(v[1], v[5]); dft2<INV>(v[2], v[6]); dft2<INV>(v[3], v[7]);
+  // twiddles w8^k on the odd half: 1, (1-i)/sqrt2, -i, (-1-i)/sqrt2   (conjugated for the inverse)
+  v[5] = INV ? make_float2(h * (v[5].x - v[5].y), h * (v[5].x + v[5].y)) : make_float2(h * (v[5].x + v[5].y), h * (v[5].y - v[5].x));
+  v[6] = rot90<INV>(v[6]);
+  v[7] = INV ? make_float2(h * (-v[7].x - v[7].y), h * (v[7].x - v[7].y)) : make_float2(h * (v[7].y - v[7].x), h * (-v[7].x - v[7].y));
+  dft2<INV>(v[0], v[2]); dft2<INV>(v[1], v[3]); dft2<INV>(v[4], v[6]); dft2<INV>(v[5], v[7]);
+  v[3] = rot90<INV>(v[3]); v[7] = rot90<INV>(v[7]);
+  dft2<INV>(v[0], v[1]); dft2<INV>(v[2], v[3]); dft2<INV>(v[4], v[5]); dft2<INV>(v[6], v[7]);
+  // outputs are in bit-reversed order 0,4,2,6,1,5,3,7
+  float2 t;
+  t = v[1]; v[1] = v[4]; v[4] = t;
+  t = v[3]; v[3] = v[6]; v[6] = t;
+}
+
+// One Stockham stage of radix R over `n` points: src -> dst.  `mul` (optional) is multiplied into
+// the inputs as they are read (the filter's spectrum).
+template <int R, bool INV>
+__device__ __forceinline__ void stage(const float2 *__restrict__ src, float2 *__restrict__ dst, const int n, const int Ns,
+                                      const float2 *__restrict__ tw, const float2 *__restrict__ mul) {
+  const int nb = n / R;
+  const int tstep = n / (Ns * R);            // index step of w = exp(-2 pi i/(Ns R)) in the n-th root table
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    float2 v[R];
+    const int k = j & (Ns - 1);              // j mod Ns (Ns is a power of two)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 a = src[j + r * nb];
+      if (mul) a = cmulf(a, __ldg(mul + j + r * nb));
+      if (r > 0 && k > 0) {
+        float2 w = __ldg(tw + r * k * tstep);
+        if (INV) w.y = -w.y;
+        a = cmulf(a, w);
+      }
+      v[r] = a;
+    }
+    if (R == 2) dft2<INV>(v[0], v[1]);
+    else if (R == 4) dft4<INV>(v);
+    else dft8<INV>(v);
+    const int base = (j - k) * R + k;        // (j div Ns) Ns R + (j mod Ns)
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[base + r * Ns] = v[r];
+  }
+}
+
+// All stages of an n-point transform (n = 2^log2n): radix 8 while possible, then 4 or 2.
+// Returns the buffer holding the result.  `keep` (optional): never written, used for `a` on entry
+// when the caller needs the input preserved (then results alternate between b and c).
+template <bool INV>
+__device__ float2 *fft_smem(float2 *a, float2 *b, float2 *c, const int n, const int log2n, const float2 *tw, const float2 *mul) {
+  int Ns = 1, left = log2n;
+  const float2 *src = a;
+  float2 *dst = b;
+  bool first = true;
+  while (left > 0) {
+    const float2 *m = first ? mul : nullptr;
+    if (left >= 3 && left != 4) { stage<8, INV>(src, dst, n, Ns, tw, m); Ns *= 8; left -= 3; }
+    else if (left >= 2) { stage<4, INV>(src, dst, n, Ns, tw, m); Ns *= 4; left -= 2; }
+    else { stage<2, INV>(src, dst, n, Ns, tw, m); Ns *= 2; left -= 1; }
+    __syncthreads();
+    first = false;
+    src = dst;
+    dst = (dst == b) ? (c ? c : a) : b;
+  }
+  return const_cast<float2 *>(src);
+}
+
+// ---- batched plain FFT (FFTPlan<float>::operator()) ---------------------------------------------
+__global__ void __launch_bounds__(1024) fft_batch_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const int n,
+                                                          const int log2n, const int inverse, const float2 *__restrict__ tw) {
+  extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+  float2 *a = (float2 *)fft_smem_raw, *b = a + n;
+  const float2 *x = in + (size_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = x[i];
+  __syncthreads();
+  float2 *r = inverse ? fft_smem<true>(a, b, nullptr, n, log2n, tw, nullptr) : fft_smem<false>(a, b, nullptr, n, log2n, tw, nullptr);
+  float2 *y = out + (size_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = r[i];
+}
+
+// ---- fused overlap-save filter bank -----------------------------------------------------------------
+// CTA b: X = FFT_2N([block b-1 | block b]); for every filter f: y = IFFT_2N(X K_f); out_f[block b] =
+// y[N..2N) / 2N.  Block -1 is the carried history (the last N samples of the previous call).
+__global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
+  extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+  const int N = a.block, n = 2 * N;
+  float2 *s0 = (float2 *)fft_smem_raw, *s1 = s0 + n, *s2 = s1 + n;
+  const int b = blockIdx.x;
+  const float2 *x = (const float2 *)a.x;
+  const float2 *prev = b == 0 ? (const float2 *)a.hist_in : x + (size_t)(b - 1) * N;
+  const float2 *cur = x + (size_t)b * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { s0[i] = prev[i]; s0[N + i] = cur[i]; }
+  if (b == (int)gridDim.x - 1) {             // roll the history: the last block of this call
+    float2 *ho = (float2 *)a.hist_out;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ho[i] = cur[i];
+  }
+  __syncthreads();
+  const float2 *tw = (const float2 *)a.tw;
+  float2 *X = fft_smem<false>(s0, s1, nullptr, n, a.log2n, tw, nullptr);    // lands in s0 or s1
+  float2 *w1 = (X == s0) ? s1 : s0;
+  const float sc = 1.0f / (float)n;
+  for (int f = 0; f < a.n_filters; ++f) {
+    const float2 *K = (const float2 *)a.kern + (size_t)f * n;
+    // X is only read (first stage, with the spectrum multiplied in); later stages alternate w1 <-> s2
+    float2 *y = fft_smem<true>(X, w1, s2, n, a.log2n, tw, K);
+    float2 *o = (float2 *)a.out + (size_t)f * a.out_stride + (size_t)b * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const float2 v = y[N + i]; o[i] = make_float2(v.x * sc, v.y * sc); }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st) {
+  if (batch == 0) return SDRG_OK;
+  const size_t smem = (size_t)2 * n * sizeof(float2);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    SDRG_CUDA(cudaFuncSetAttribute(fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  int threads = n / 8; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
+  fft_batch_kernel<<<(unsigned)batch, threads, smem, st>>>((const float2 *)in, (float2 *)out, n, log2n, inverse, (const float2 *)tw);
+  SDRG_CHECK_LAUNCH("fft_batch_kernel");
+  return SDRG_OK;
+}
+
+int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
+  if (n_blocks == 0) return SDRG_OK;
+  const int n = 2 * a.block;
+  const size_t smem = (size_t)3 * n * sizeof(float2);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    SDRG_CUDA(cudaFuncSetAttribute(filter_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  int threads = n / 8; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
+  filter_ola_kernel<<<(unsigned)n_blocks, threads, smem, st>>>(a);
+  SDRG_CHECK_LAUNCH("filter_ola_kernel");
+  return SDRG_OK;
+}
+
+}  // namespace sdrg

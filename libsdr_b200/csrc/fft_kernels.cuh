@@ -1,0 +1,25 @@
+// fft_kernels.cuh -- launch wrappers of the shared-memory FFT and the fused FFT-convolution filter.
+#pragma once
+#include "common.cuh"
+
+namespace sdrg {
+
+constexpr int kFftMaxLog2 = 13;          // one CTA holds up to 8192 points (3 x 64 KB for the filter)
+
+struct FilterArgs {
+  const void *x;          // n_blocks x block complex floats
+  const void *hist_in;    // the previous call's last block
+  void       *hist_out;
+  const void *kern;       // n_filters x 2*block spectra (already divided by their l2 norm)
+  void       *out;        // filter f writes block b to out + f*out_stride + b*block
+  size_t      out_stride; // in samples
+  const void *tw;         // 2*block-th roots of unity, exp(-2 pi i k / (2 block))
+  int         block;
+  int         log2n;      // log2(2*block)
+  int         n_filters;
+};
+
+int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st);
+int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st);
+
+}  // namespace sdrg

@@ -266,3 +266,99 @@ class RxChain:
         _lib.call("sdrg_rxchain_process", self._h, _np_ptr(x), buffer_size, nb, _np_ptr(bb_out),
                   _np_ptr(audio_out), n_out, C.byref(got), counts)
         return bb_out[:got.value], audio_out[:got.value], np.array(counts[:], dtype=np.int64)
+
+
+class FFTPlan:
+    """FFTPlan<float> (src/fftplan_fftw3.hh:79-142): FFTPlan(n, direction) with direction FORWARD/BACKWARD;
+    calling the plan transforms `batch` contiguous n-point signals (complex64)."""
+    FORWARD, BACKWARD = 0, 1
+
+    def __init__(self, n, direction):
+        self.n = int(n)
+        self._h = C.c_void_p()
+        _lib.call("sdrg_fft_create", self.n, int(direction), C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_fft_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def __call__(self, x):
+        if _is_torch(x):
+            import torch
+            out = torch.empty_like(x)
+            _lib.call("sdrg_fft_exec_dev", self._h, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                      x.numel() // self.n, _stream_ptr())
+            return out
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.empty_like(x)
+        _lib.call("sdrg_fft_exec", self._h, _np_ptr(x), _np_ptr(out), x.size // self.n)
+        return out
+
+
+class FilterNode:
+    """FilterNode<float>(block_size) (src/filternode.hh:231-283): addFilter(fmin, fmax) returns the
+    filter's index; process(x) returns an array (n_filters, n_out) of complex64."""
+
+    def __init__(self, block_size=1024):
+        self.block = int(block_size)
+        self._h = C.c_void_p()
+        _lib.call("sdrg_filter_create", self.block, C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_filter_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def addFilter(self, fmin, fmax):
+        idx = C.c_size_t(0)
+        _lib.call("sdrg_filter_add", self._h, float(fmin), float(fmax), C.byref(idx))
+        return idx.value
+
+    def setFreq(self, index, fmin, fmax):
+        _lib.call("sdrg_filter_set_freq", self._h, int(index), float(fmin), float(fmax))
+
+    def n_filters(self):
+        n = C.c_size_t(0)
+        _lib.call("sdrg_filter_count", self._h, C.byref(n))
+        return n.value
+
+    def config(self, src_cfg=None, *, sample_rate=0.0, buffer_size=0, num_buffers=1, type=T_CF32):
+        if src_cfg is None:
+            src_cfg = Config(type, sample_rate, buffer_size, num_buffers)
+        out = Config()
+        _lib.call("sdrg_filter_configure", self._h, C.byref(src_cfg), C.byref(out))
+        return out
+
+    def design(self, index):
+        kern = np.zeros(2 * self.block, dtype=np.complex64); taps = np.zeros(self.block, dtype=np.complex64)
+        _lib.call("sdrg_filter_get_design", self._h, int(index), _np_ptr(kern), _np_ptr(taps))
+        return kern, taps
+
+    def outputs_for(self, n_in):
+        n = C.c_size_t(0)
+        _lib.call("sdrg_filter_outputs_for", self._h, int(n_in), C.byref(n))
+        return n.value
+
+    def process(self, x):
+        F = max(self.n_filters(), 1)
+        got = C.c_size_t(0)
+        if _is_torch(x):
+            import torch
+            n_in = x.shape[0]
+            n_out = self.outputs_for(n_in)
+            out = torch.empty((F, max(n_out, 1)), dtype=torch.complex64, device=x.device)
+            _lib.call("sdrg_filter_process_dev", self._h, C.c_void_p(x.data_ptr()), n_in, C.c_void_p(out.data_ptr()),
+                      max(n_out, 1), C.byref(got), _stream_ptr())
+            return out[:, :got.value]
+        x = np.ascontiguousarray(x, dtype=np.complex64).reshape(-1)
+        n_out = self.outputs_for(x.shape[0])
+        out = np.zeros((F, max(n_out, 1)), dtype=np.complex64)
+        _lib.call("sdrg_filter_process", self._h, _np_ptr(x), x.shape[0], _np_ptr(out), max(n_out, 1), C.byref(got))
+        return out[:, :got.value]
