@@ -200,6 +200,23 @@ int sdrg_filter_process(sdrg_filter *h, const void *in, size_t n_in, void *out, 
 int sdrg_filter_process_dev(sdrg_filter *h, const void *d_in, size_t n_in, void *d_out, size_t out_stride,
                             size_t *n_out, void *stream);
 
+/* ---- channel bank: C independent IQBaseBand<Scalar> nodes on ONE input stream, each followed by
+ *      FM / AM / USB demodulators connected out of place (several sinks on one source,
+ *      src/node.cc:75).  Channel c equals IQBaseBand<Scalar>(Fc[c], Ff[c], width, order, sub_sample, oFs)
+ *      (src/baseband.hh:47-57) bit for bit; Ff == NULL means Ff = Fc.  scalar: SDRG_T_S8 / SDRG_T_S16.
+ *      Outputs of channel c land at <ptr> + c*out_stride elements; any output pointer may be NULL. -- */
+typedef struct sdrg_bank sdrg_bank;
+int sdrg_bank_create(int scalar, size_t n_channels, const double *Fc, const double *Ff, double width, size_t order,
+                     size_t sub_sample, double oFs, sdrg_bank **h);
+int sdrg_bank_destroy(sdrg_bank *h);
+int sdrg_bank_configure(sdrg_bank *h, const sdrg_config *src, sdrg_config *out);
+int sdrg_bank_get_info(const sdrg_bank *h, size_t *channels, size_t *sub_sample, size_t channel, sdrg_iqbb_info *info, void *kernel);
+int sdrg_bank_outputs_for(const sdrg_bank *h, size_t n_in, size_t *n_out);
+int sdrg_bank_process(sdrg_bank *h, const void *in, size_t buffer_size, size_t n_buffers, void *bb, void *fm, void *am,
+                      void *usb, size_t out_stride, size_t *n_out);
+int sdrg_bank_process_dev(sdrg_bank *h, const void *d_in, size_t buffer_size, size_t n_buffers, void *d_bb, void *d_fm,
+                          void *d_am, void *d_usb, size_t out_stride, size_t *n_out, void *stream);
+
 /* number of kernels the library has launched so far (all handles, this process) */
 int sdrg_kernel_launch_count(uint64_t *count);
 

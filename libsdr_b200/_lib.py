@@ -114,6 +114,13 @@ SIGNATURES = {
     "sdrg_filter_outputs_for": [_V, _SZ, _PSZ],
     "sdrg_filter_process": [_V, _V, _SZ, _V, _SZ, _PSZ],
     "sdrg_filter_process_dev": [_V, _V, _SZ, _V, _SZ, _PSZ, _V],
+    "sdrg_bank_create": [_I, _SZ, C.POINTER(C.c_double), C.POINTER(C.c_double), _D, _SZ, _SZ, _D, _PV],
+    "sdrg_bank_destroy": [_V],
+    "sdrg_bank_configure": [_V, _PCFG, _PCFG],
+    "sdrg_bank_get_info": [_V, _PSZ, _PSZ, _SZ, C.POINTER(IqbbInfo), _V],
+    "sdrg_bank_outputs_for": [_V, _SZ, _PSZ],
+    "sdrg_bank_process": [_V, _V, _SZ, _SZ, _V, _V, _V, _V, _SZ, _PSZ],
+    "sdrg_bank_process_dev": [_V, _V, _SZ, _SZ, _V, _V, _V, _V, _SZ, _PSZ, _V],
     "sdrg_kernel_launch_count": [C.POINTER(C.c_uint64)],
     "sdrg_profile_enable": [_I],
     "sdrg_profile_read": [_I, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],

@@ -157,23 +157,8 @@ int grow(void **p, size_t *cap, size_t need) {
 
 void free_dev(void **p) { if (*p) { cudaFree(*p); *p = nullptr; } }
 
-// Window grid in closed form.  With c = samples consumed since config(), global
-// sample n carries the window counter q(n) = max(n,1)-1 (window 0 holds ss+1 samples because
-// _sample_count is incremented after the test, baseband.hh:200,212-217); a window completes at every
-// n >= 1 with n % ss == 0.  ss == 1 degenerates to one output per sample (baseband.hh:218-219).
-struct Advance { uint64_t n_out; uint32_t r0; uint32_t first; uint32_t e0; };
-uint64_t windows_done(uint64_t c, uint64_t ss) { return ss == 1 ? c : (c ? (c - 1) / ss : 0); }
-Advance advance(const sdrg_iqbb *h, uint64_t n) {
-  const uint64_t ss = h->d.sub_sample, c = h->consumed;
-  Advance a{};
-  a.n_out = windows_done(c + n, ss) - windows_done(c, ss);
-  if (ss == 1) { a.r0 = 0; a.first = 0; a.e0 = 0; return a; }
-  a.first = c == 0 ? 1u : 0u;
-  a.r0 = c ? (uint32_t)((c - 1) % ss) : 0u;
-  const uint64_t lo = c ? c : 1;                           // first global index that can complete
-  a.e0 = (uint32_t)(((lo + ss - 1) / ss) * ss - c);
-  return a;
-}
+typedef WindowAdvance Advance;
+Advance advance(const sdrg_iqbb *h, uint64_t n) { return window_advance(h->consumed, h->d.sub_sample, n); }
 
 // Folded float path: A(a) and U(r,e) in double on the host (see iqbb_fold_kernels.cu).
 int upload_fold_tables(sdrg_iqbb *h) {

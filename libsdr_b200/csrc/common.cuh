@@ -69,4 +69,21 @@ void design_lut(IqbbDesign &d);
 void design_kernel(IqbbDesign &d);
 void design_lut_increment(IqbbDesign &d, double nco_Fs);
 
+// Window grid in closed form.  With c = samples consumed since config(), global
+// sample n carries the window counter q(n) = max(n,1)-1 (window 0 holds ss+1 samples because
+// _sample_count is incremented after the test, baseband.hh:200,212-217); a window completes at every
+// n >= 1 with n % ss == 0.  ss == 1 degenerates to one output per sample (baseband.hh:218-219).
+struct WindowAdvance { uint64_t n_out; uint32_t r0; uint32_t first; uint32_t e0; };
+static inline uint64_t windows_done(uint64_t c, uint64_t ss) { return ss == 1 ? c : (c ? (c - 1) / ss : 0); }
+static inline WindowAdvance window_advance(uint64_t c, uint64_t ss, uint64_t n) {
+  WindowAdvance a{};
+  a.n_out = windows_done(c + n, ss) - windows_done(c, ss);
+  if (ss == 1) { a.r0 = 0; a.first = 0; a.e0 = 0; return a; }
+  a.first = c == 0 ? 1u : 0u;
+  a.r0 = c ? (uint32_t)((c - 1) % ss) : 0u;
+  const uint64_t lo = c ? c : 1;                           // first global index that can complete
+  a.e0 = (uint32_t)(((lo + ss - 1) / ss) * ss - c);
+  return a;
+}
+
 }  // namespace sdrg

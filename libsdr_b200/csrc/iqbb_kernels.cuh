@@ -70,7 +70,25 @@ struct IqbbFinalizeArgs {
   uint32_t    in_place;   // FM: what element 0 of every segment shows
 };
 
+// One process() call of a channel bank (bank_kernels.cu); window geometry as in IqbbAccumArgs
+struct BankAccumArgs {
+  const void     *x, *hist_in;
+  void           *hist_out;
+  const void     *taps;       // channels x taps_len int4 (Gauss form)
+  const void     *lut;        // 128 x int2 (shared by all channels)
+  const uint32_t *inc;        // per channel: lut_inc (0 = mixer bypassed)
+  const uint32_t *neg;        // per channel: negative shift
+  void           *acc_cur, *acc_next;   // channels x acc_stride accumulators (int2)
+  size_t          acc_stride;
+  uint32_t        n, channels, group, taps_len, hist_len, ss, r0, first;
+  uint32_t        consumed15; // samples consumed since config(), mod 32768 (NCO phase = consumed*inc mod 32768)
+  uint32_t        zero_next;
+};
+struct BankFinalizeStrides { size_t acc_stride, out_stride; uint32_t bb_bytes, audio_bytes; };
+
 int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st);
+int launch_bank_accum(int scalar, const BankAccumArgs &a, cudaStream_t st);
+int launch_bank_finalize(int scalar, const IqbbFinalizeArgs &a, const BankFinalizeStrides &s, uint32_t channels, cudaStream_t st);
 int launch_iqbb_finalize(int scalar, const IqbbFinalizeArgs &a, cudaStream_t st);
 int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st);
 

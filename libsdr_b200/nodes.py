@@ -362,3 +362,78 @@ class FilterNode:
         out = np.zeros((F, max(n_out, 1)), dtype=np.complex64)
         _lib.call("sdrg_filter_process", self._h, _np_ptr(x), x.shape[0], _np_ptr(out), max(n_out, 1), C.byref(got))
         return out[:, :got.value]
+
+
+class ChannelBank:
+    """C independent IQBaseBand<Scalar>(Fc[c], Ff[c], width, order, sub_sample, oFs) nodes on one input
+    stream, each with FM/AM/USB demodulators connected out of place (sdrg_bank_*)."""
+
+    def __init__(self, scalar, Fc, Ff, width, order, sub_sample, oFs=0.0):
+        self.scalar = scalar_id(scalar)
+        self.dtype = _NP[self.scalar]
+        Fc = np.ascontiguousarray(Fc, dtype=np.float64)
+        Ff = Fc if Ff is None else np.ascontiguousarray(Ff, dtype=np.float64)
+        self.channels = Fc.shape[0]
+        self._h = C.c_void_p()
+        dp = C.POINTER(C.c_double)
+        _lib.call("sdrg_bank_create", self.scalar, self.channels, Fc.ctypes.data_as(dp), Ff.ctypes.data_as(dp),
+                  float(width), int(order), int(sub_sample), float(oFs), C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_bank_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def config(self, src_cfg=None, *, sample_rate=0.0, buffer_size=0, num_buffers=1, type=None):
+        if src_cfg is None:
+            src_cfg = Config(_CTYPE[self.scalar] if type is None else type, sample_rate, buffer_size, num_buffers)
+        out = Config()
+        _lib.call("sdrg_bank_configure", self._h, C.byref(src_cfg), C.byref(out))
+        return out
+
+    def outputs_for(self, n_in):
+        n = C.c_size_t(0)
+        _lib.call("sdrg_bank_outputs_for", self._h, int(n_in), C.byref(n))
+        return n.value
+
+    def channel_info(self, c):
+        inf = _lib.IqbbInfo()
+        k = np.zeros((1024, 2), dtype=np.int32)
+        _lib.call("sdrg_bank_get_info", self._h, None, None, int(c), C.byref(inf), _np_ptr(k))
+        return inf, k[:inf.order]
+
+    def process(self, x, buffer_size, want=("bb", "fm", "am", "usb"), out=None):
+        """x: (n_buffers*buffer_size, 2). Returns dict name -> (channels, n_out) array/tensor."""
+        n_total = x.shape[0]
+        assert n_total % buffer_size == 0
+        nb = n_total // buffer_size
+        n_out = self.outputs_for(n_total)
+        stride = max(n_out, 1)
+        got = C.c_size_t(0)
+        res = {} if out is None else out
+        if _is_torch(x):
+            import torch
+            tdt = {np.int16: torch.int16, np.int8: torch.int8}[self.dtype]
+            shapes = {"bb": ((self.channels, stride, 2), tdt), "fm": ((self.channels, stride), torch.int16),
+                      "am": ((self.channels, stride), tdt), "usb": ((self.channels, stride), tdt)}
+            for k in want:
+                if k not in res:
+                    res[k] = torch.zeros(shapes[k][0], dtype=shapes[k][1], device=x.device)
+            stride = res[want[0]].shape[1]
+            ptr = lambda k: C.c_void_p(res[k].data_ptr()) if k in want else None  # noqa: E731
+            _lib.call("sdrg_bank_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb, ptr("bb"), ptr("fm"),
+                      ptr("am"), ptr("usb"), stride, C.byref(got), _stream_ptr())
+            return {k: res[k][:, :got.value] for k in want}
+        x = np.ascontiguousarray(x, dtype=self.dtype).reshape(-1, 2)
+        shapes = {"bb": ((self.channels, stride, 2), self.dtype), "fm": ((self.channels, stride), np.int16),
+                  "am": ((self.channels, stride), self.dtype), "usb": ((self.channels, stride), self.dtype)}
+        for k in want:
+            if k not in res:
+                res[k] = np.zeros(shapes[k][0], dtype=shapes[k][1])
+        ptr = lambda k: _np_ptr(res[k]) if k in want else None  # noqa: E731
+        _lib.call("sdrg_bank_process", self._h, _np_ptr(x), buffer_size, nb, ptr("bb"), ptr("fm"), ptr("am"), ptr("usb"),
+                  stride, C.byref(got))
+        return {k: res[k][:, :got.value] for k in want}
