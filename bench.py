@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[1], "c2"): IQBaseBand<float>(64 taps, shift 100 kHz, 20 MS/s ->
 48 kHz) + FMDemod on complex-float IQ; one "step" = one pass of the fused chain over a batch of
-64 buffers of 2^20 samples (64 Mi samples, 512 MiB > L2, so every step streams from HBM).
+256 buffers of 2^20 samples (256 Mi samples, 2 GiB > L2, so every step streams from HBM).
 Metric: input IQ Msamples/s.
 
   value    : device-resident throughput (inputs already in HBM), CUDA events, max over ranks
@@ -40,6 +40,7 @@ UNIT = "Msamples/s"
 
 def workload():
     c = dict(synth.C2)
+    c["n_buffers"] = 256        # one step = 256 buffers of 2^20 samples = 2 GiB of cf32 per GPU
     return c
 
 
@@ -169,6 +170,96 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def _time_steps(fn, steps, warmup, barrier):
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def secondary_workloads(world, rank, dev, dist, args):
+    """Short measurements of the other BASELINE configs (not the headline line): the sharded
+    2048-channel bank (C5) on all ranks, and -- single GPU only -- the int16 chain (C1) and the FFT filter (C3)."""
+    import torch
+    from libsdr_b200 import parallel
+    from libsdr_b200.nodes import ChannelBank, IQBaseBand, RxChain, FilterNode, DEMOD_FM
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxms(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    try:   # C5: 2048 channels sharded by contiguous channel ranges, outputs gathered with NCCL
+        c = dict(synth.C5)
+        bs, nb = c["buffer_size"], 2
+        fc_all = synth.bank_frequencies(c["channels"], c["Fs"])
+        fc, lo, hi = parallel.bank_frequencies_for_rank(rank, world, fc_all)
+        x = torch.from_numpy(synth.bank_input(bs, dict(c, channels=16))).to(dev).repeat(nb, 1)
+        bank = ChannelBank("s16", fc, None, c["width"], c["order"], c["sub_sample"], c["oFs"])
+        bank.config(sample_rate=c["Fs"], buffer_size=bs)
+        n_out = bank.outputs_for(bs * nb) + 1
+        bufs = {"fm": torch.zeros((hi - lo, n_out), dtype=torch.int16, device=dev),
+                "am": torch.zeros((hi - lo, n_out), dtype=torch.int16, device=dev)}
+
+        def step():
+            r = bank.process(x, bs, want=("fm", "am"), out=bufs)
+            if world > 1:
+                parallel.gather_channel_outputs(bufs["fm"], c["channels"])
+                parallel.gather_channel_outputs(bufs["am"], c["channels"])
+            return r
+
+        ms = maxms(_time_steps(step, 3, 2, barrier))
+        out["c5_bank"] = {"workload": "2048-channel IQBaseBand<int16> bank (15 taps, 100 MS/s -> 48 kHz) + FM + AM, channels "
+                                      "sharded over %d GPU(s), NCCL all_gather of the audio" % world,
+                          "input_msamples_per_s": bs * nb / ms / 1e3, "channel_msamples_per_s": c["channels"] * bs * nb / ms / 1e3,
+                          "ms_per_step": ms, "buffers_per_step": nb, "scaling": "strong (channels fixed)"}
+    except Exception as e:  # pragma: no cover
+        out["c5_bank"] = {"error": str(e)[:200]}
+    if world > 1 or args.no_secondary:
+        return out
+    try:   # C1: int16, 15 taps, 2.4 MS/s -> 48 kHz + FM
+        c = dict(synth.C1)
+        bs, nb = c["buffer_size"], 2048
+        x = torch.from_numpy(synth.c1_input(16 * bs)).to(dev).repeat(nb // 16, 1)
+        bb = IQBaseBand("s16", c["Fc"], c["Ff"], c["width"], c["order"], c["sub_sample"], c["oFs"])
+        bb.config(sample_rate=c["Fs"], buffer_size=bs)
+        ch = RxChain(bb, DEMOD_FM)
+        ms = _time_steps(lambda: ch.process(x, bs), 5, 2, barrier)
+        out["c1_int16"] = {"workload": "IQBaseBand<int16> 15 taps, 2.4 MS/s -> 48 kHz + FMDemod, %d buffers of %d" % (nb, bs),
+                           "msamples_per_s": bs * nb / ms / 1e3, "ms_per_step": ms,
+                           "algorithmic_gbs": (4 + 2 / 50) * bs * nb / ms / 1e6, "bound": "integer multiply issue (bit-exact path)"}
+    except Exception as e:  # pragma: no cover
+        out["c1_int16"] = {"error": str(e)[:200]}
+    try:   # C3: FFT-convolution filter, block 4096
+        c = dict(synth.C3)
+        nb = c["n_buffers"]
+        x = torch.from_numpy(synth.c2_input(c["buffer_size"])).to(dev).repeat(nb, 1).view(torch.complex64).reshape(-1)
+        f = FilterNode(c["block"]); f.addFilter(c["fmin"], c["fmax"]); f.config(sample_rate=c["Fs"], buffer_size=c["block"])
+        ms = _time_steps(lambda: f.process(x), 5, 2, barrier)
+        n = x.shape[0]
+        out["c3_filter"] = {"workload": "FilterNode<float> block 4096 (FFT 8192), 1 band-pass filter, %d buffers of 2^20" % nb,
+                            "msamples_per_s": n / ms / 1e3, "ms_per_step": ms, "algorithmic_gbs": 16 * n / ms / 1e6,
+                            "bound": "shared memory / FP32 (Stockham FFT)"}
+    except Exception as e:  # pragma: no cover
+        out["c3_filter"] = {"error": str(e)[:200]}
+    return out
+
+
 # ---- our arm -----------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -177,6 +268,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short C1/C3 side measurements")
     ap.add_argument("--buffers", type=int, default=0, help="buffers per step (default: the workload's n_buffers)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -262,7 +354,7 @@ def main():
     x_np = x_host.numpy()
     n_out = bb.outputs_for(n_step)
     audio_host = torch.zeros(n_out + 1, dtype=torch.float32).pin_memory().numpy()
-    K2 = max(3, min(K, 10))
+    K2 = max(3, min(K, 5))
 
     def step_e2e():
         got = C.c_size_t(0)
@@ -285,6 +377,7 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * n_step * K2 / e2e_s / 1e6
     clocks = sampler.stop() if rank == 0 else None
+    secondary = secondary_workloads(world, rank, dev, dist, args)
 
     if rank == 0:
         peaks = {}
@@ -314,7 +407,7 @@ def main():
                              "kernel_ms": k_ms, "kernel_launches": int(acc_n),
                              "kernel_share_of_step": (acc_ms / ms) if ms > 0 else None,
                              "finalize_ms": fin_ms / max(fin_n, 1)},
-                "clocks": clocks}
+                "clocks": clocks, "secondary": secondary}
         if world == 1 and not args.no_cpu_baseline:
             nbuf = 24
             v, dt = cpu_port_run(c, x_np, 1, nbuf)
