@@ -308,13 +308,25 @@ def main():
     ss = bb.info().sub_sample
     n_out_cap = n_step // ss + 2
     bb_out = torch.empty((n_out_cap, 2), dtype=torch.float32, device=dev)
-    audio = torch.zeros(n_out_cap, dtype=torch.float32, device=dev)
-    gathered = torch.empty(world * n_out_cap, dtype=torch.float32, device=dev) if world > 1 else None
+    # double-buffered audio so that the NCCL gather of step k overlaps the kernels of step k+1
+    audio2 = [torch.zeros(n_out_cap, dtype=torch.float32, device=dev) for _ in range(2)]
+    gathered2 = [torch.empty(world * n_out_cap, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    counter = [0]
 
     def step_dev():
-        chain.process(x_dev, bs, bb_out=bb_out, audio_out=audio)
+        k = counter[0] & 1
+        counter[0] += 1
+        if pending[k] is not None:
+            pending[k].wait()                       # the gather that last read audio2[k] has finished
+        chain.process(x_dev, bs, bb_out=bb_out, audio_out=audio2[k])
         if world > 1:
-            dist.all_gather_into_tensor(gathered, audio)
+            pending[k] = dist.all_gather_into_tensor(gathered2[k], audio2[k], async_op=True)
+
+    def drain():
+        for w in pending:
+            if w is not None:
+                w.wait()
 
     def barrier():
         if world > 1:
@@ -323,6 +335,7 @@ def main():
 
     for _ in range(W):
         step_dev()
+    drain()
     barrier()
 
     sampler = ClockSampler(local)
@@ -337,6 +350,7 @@ def main():
     ev0.record()
     for _ in range(K):
         step_dev()
+    drain()
     ev1.record()
     barrier()
     launches = _lib.kernel_launch_count() - l0

@@ -52,6 +52,11 @@ template <bool INV> __device__ __forceinline__ void dft8(float2 *v) {
   t = v[3]; v[3] = v[6]; v[6] = t;
 }
 
+// Shared-memory index padding: one spare element after every 8 keeps the strided writes of the
+// early stages (stride 8 and 64 elements) off the same banks (8-byte elements, 32 x 4-byte banks).
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 3) + 8; }
+
 // One Stockham stage of radix R over `n` points: src -> dst.  `mul` (optional) is multiplied into
 // the inputs as they are read (the filter's spectrum).
 template <int R, bool INV>
@@ -64,21 +69,29 @@ __device__ __forceinline__ void stage(const float2 *__restrict__ src, float2 *__
     const int k = j & (Ns - 1);              // j mod Ns (Ns is a power of two)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float2 a = src[j + r * nb];
-      if (mul) a = cmulf(a, __ldg(mul + j + r * nb));
-      if (r > 0 && k > 0) {
-        float2 w = __ldg(tw + r * k * tstep);
-        if (INV) w.y = -w.y;
-        a = cmulf(a, w);
+      v[r] = src[pidx(j + r * nb)];
+      if (mul) v[r] = cmulf(v[r], __ldg(mul + j + r * nb));
+    }
+    if (k > 0) {
+      // w^r for r = 1..R-1 from ONE table load: w2 = w w, w3 = w2 w, w4 = w2 w2, ... (depth <= 3)
+      float2 w1 = __ldg(tw + k * tstep);
+      if (INV) w1.y = -w1.y;
+      v[1] = cmulf(v[1], w1);
+      if (R > 2) {
+        const float2 w2 = cmulf(w1, w1), w3 = cmulf(w2, w1);
+        v[2] = cmulf(v[2], w2); v[3] = cmulf(v[3], w3);
+        if (R > 4) {
+          const float2 w4 = cmulf(w2, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
+          v[4] = cmulf(v[4], w4); v[5] = cmulf(v[5], w5); v[6] = cmulf(v[6], w6); v[7] = cmulf(v[7], w7);
+        }
       }
-      v[r] = a;
     }
     if (R == 2) dft2<INV>(v[0], v[1]);
     else if (R == 4) dft4<INV>(v);
     else dft8<INV>(v);
     const int base = (j - k) * R + k;        // (j div Ns) Ns R + (j mod Ns)
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[base + r * Ns] = v[r];
+    for (int r = 0; r < R; ++r) dst[pidx(base + r * Ns)] = v[r];
   }
 }
 
@@ -108,13 +121,13 @@ __device__ float2 *fft_smem(float2 *a, float2 *b, float2 *c, const int n, const 
 __global__ void __launch_bounds__(1024) fft_batch_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const int n,
                                                           const int log2n, const int inverse, const float2 *__restrict__ tw) {
   extern __shared__ __align__(16) unsigned char fft_smem_raw[];
-  float2 *a = (float2 *)fft_smem_raw, *b = a + n;
+  float2 *a = (float2 *)fft_smem_raw, *b = a + padded_len(n);
   const float2 *x = in + (size_t)blockIdx.x * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = x[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[pidx(i)] = x[i];
   __syncthreads();
   float2 *r = inverse ? fft_smem<true>(a, b, nullptr, n, log2n, tw, nullptr) : fft_smem<false>(a, b, nullptr, n, log2n, tw, nullptr);
   float2 *y = out + (size_t)blockIdx.x * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = r[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = r[pidx(i)];
 }
 
 // ---- fused overlap-save filter bank -----------------------------------------------------------------
@@ -123,12 +136,12 @@ __global__ void __launch_bounds__(1024) fft_batch_kernel(const float2 *__restric
 __global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
   extern __shared__ __align__(16) unsigned char fft_smem_raw[];
   const int N = a.block, n = 2 * N;
-  float2 *s0 = (float2 *)fft_smem_raw, *s1 = s0 + n, *s2 = s1 + n;
+  float2 *s0 = (float2 *)fft_smem_raw, *s1 = s0 + padded_len(n), *s2 = s1 + padded_len(n);
   const int b = blockIdx.x;
   const float2 *x = (const float2 *)a.x;
   const float2 *prev = b == 0 ? (const float2 *)a.hist_in : x + (size_t)(b - 1) * N;
   const float2 *cur = x + (size_t)b * N;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) { s0[i] = prev[i]; s0[N + i] = cur[i]; }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { s0[pidx(i)] = prev[i]; s0[pidx(N + i)] = cur[i]; }
   if (b == (int)gridDim.x - 1) {             // roll the history: the last block of this call
     float2 *ho = (float2 *)a.hist_out;
     for (int i = threadIdx.x; i < N; i += blockDim.x) ho[i] = cur[i];
@@ -143,7 +156,7 @@ __global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
     // X is only read (first stage, with the spectrum multiplied in); later stages alternate w1 <-> s2
     float2 *y = fft_smem<true>(X, w1, s2, n, a.log2n, tw, K);
     float2 *o = (float2 *)a.out + (size_t)f * a.out_stride + (size_t)b * N;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { const float2 v = y[N + i]; o[i] = make_float2(v.x * sc, v.y * sc); }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const float2 v = y[pidx(N + i)]; o[i] = make_float2(v.x * sc, v.y * sc); }
     __syncthreads();
   }
 }
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
 
 int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st) {
   if (batch == 0) return SDRG_OK;
-  const size_t smem = (size_t)2 * n * sizeof(float2);
+  const size_t smem = (size_t)2 * padded_len(n) * sizeof(float2);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     SDRG_CUDA(cudaFuncSetAttribute(fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -167,7 +180,7 @@ int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, s
 int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
   if (n_blocks == 0) return SDRG_OK;
   const int n = 2 * a.block;
-  const size_t smem = (size_t)3 * n * sizeof(float2);
+  const size_t smem = (size_t)3 * padded_len(n) * sizeof(float2);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     SDRG_CUDA(cudaFuncSetAttribute(filter_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
