@@ -102,6 +102,7 @@ struct sdrg_iqbb {
   size_t acc_cap = 0;
   uint32_t acc_dirty[2] = {0, 0};
   uint32_t taps_len = 1, hist_len = 0;
+  std::vector<int32_t> host_taps;      // int paths: the Gauss-form taps as uploaded
   // folded float path (iqbb_fold_kernels.cu)
   int float_path = 0;                  // 0 auto, 1 direct, 2 folded
   bool fold = false;
@@ -223,11 +224,13 @@ int upload_design(sdrg_iqbb *h) {
     while (lead + 1 < L && d.k_re[lead] == 0 && d.k_im[lead] == 0) ++lead;
     const size_t Lp = L - lead;
     std::vector<int32_t> taps(4 * Lp), lut(256);
+    h->host_taps.assign(4 * Lp, 0);
     for (size_t i = 0; i < Lp; ++i) {
       const uint32_t kr = (uint32_t)d.k_re[lead + i], ki = (uint32_t)d.k_im[lead + i];
       taps[4 * i] = (int32_t)kr; taps[4 * i + 1] = (int32_t)(ki - kr); taps[4 * i + 2] = (int32_t)(kr + ki);
       taps[4 * i + 3] = 0;
     }
+    h->host_taps = taps;
     for (size_t j = 0; j < 128; ++j) { lut[2 * j] = d.lut_re[j]; lut[2 * j + 1] = d.lut_im[j]; }
     h->taps_len = (uint32_t)Lp;
     SDRG_CUDA(cudaMalloc(&h->d_taps, taps.size() * sizeof(int32_t)));
@@ -317,6 +320,7 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   IqbbAccumArgs a{};
   a.x = d_in; a.hist_in = h->d_hist[p]; a.hist_out = h->d_hist[q];
   a.taps = h->d_taps; a.lut = h->d_lut;
+  a.host_taps = (h->d.scalar != SDRG_T_F32 && !h->host_taps.empty()) ? h->host_taps.data() : nullptr;
   a.acc_cur = h->d_acc[p]; a.acc_next = h->d_acc[q];
   a.n = n; a.taps_len = h->taps_len; a.hist_len = h->hist_len;
   a.ss = (uint32_t)h->d.sub_sample; a.r0 = adv.r0; a.first = adv.first;

@@ -37,16 +37,18 @@ __device__ __forceinline__ void unpack16(uint32_t v, int &re, int &im) {
   im = ((int)v) >> 16;
 }
 
-// window bookkeeping (call-relative sample index i): q(i) = r0 + i - (first && i>0); slot = q/ss
+// window bookkeeping (call-relative sample index i): q(i) = r0 + i - (first && i>0); slot = q/ss.
+// n <= 2^30 and r0 < ss <= 2^30, so q and every window bound fit in 32 bits (the 64-bit division
+// this used to be cost more than the FIR itself).
 struct WindowGrid {
   uint32_t ss, r0, first;
-  __device__ __forceinline__ uint64_t q(uint32_t i) const { return (uint64_t)r0 + i - ((first && i > 0) ? 1u : 0u); }
-  __device__ __forceinline__ uint32_t slot(uint32_t i) const { return (uint32_t)(q(i) / ss); }
+  __device__ __forceinline__ uint32_t q(uint32_t i) const { return r0 + i - ((first && i > 0) ? 1u : 0u); }
+  __device__ __forceinline__ uint32_t slot(uint32_t i) const { return q(i) / ss; }
   __device__ __forceinline__ int64_t begin(uint32_t s) const {
-    return s == 0 ? 0 : (int64_t)((uint64_t)s * ss) - (int64_t)r0 + (int64_t)first;
+    return s == 0 ? 0 : (int64_t)(uint32_t)(s * ss - r0 + first);
   }
   __device__ __forceinline__ int64_t end(uint32_t s) const {
-    return (int64_t)((uint64_t)(s + 1) * ss) - (int64_t)r0 + (int64_t)first;
+    return (int64_t)(uint32_t)((s + 1) * ss - r0 + first);
   }
 };
 
@@ -66,6 +68,44 @@ __device__ __forceinline__ void prologue(const IqbbAccumArgs &a) {
     for (int64_t k = threadIdx.x; k < H; k += blockDim.x) {
       const int64_t i = n - H + k;                       // call-relative source index
       ho[k] = (i >= 0) ? x[i] : hi[H + i];
+    }
+  }
+}
+
+// Per-window partial sums of one tile from the transposed z staging, added into the call's
+// accumulators.  Short windows (ss <= 64: >= 32 windows per tile) take one THREAD per window --
+// the issue cost is ~3 instructions per sample of ONE warp-lane instead of a warp-wide loop per
+// window; long windows take one warp per window with a REDUX.SUM at the end.
+__device__ __forceinline__ void window_sums_int(const IqbbAccumArgs &a, const int2 *zs, const int64_t tile_base, const int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile_lo = (uint32_t)tile_base;
+  const uint32_t tile_hi = (uint32_t)min((int64_t)a.n, tile_base + kTile);
+  if (tile_hi <= tile_lo) return;
+  WindowGrid g{a.ss, a.r0, a.first};
+  const uint32_t slot_lo = g.slot(tile_lo), slot_hi = g.slot(tile_hi - 1);
+  int *acc = (int *)a.acc_cur;
+  const int t_hi = (int)(tile_hi - tile_lo);
+  if (a.ss > 64) {
+    for (uint32_t s = slot_lo + warp; s <= slot_hi; s += kT / 32) {
+      const int lo = max((int)(g.begin(s) - tile_base), 0), hi = min((int)(g.end(s) - tile_base), t_hi);
+      uint32_t sr = 0, si = 0;
+      for (int o = lo + lane; o < hi; o += 32) {
+        const int2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
+        sr += (uint32_t)z.x; si += (uint32_t)z.y;
+      }
+      sr = __reduce_add_sync(kFull, sr);
+      si = __reduce_add_sync(kFull, si);
+      if (lane == 0) { atomicAdd(acc + 2 * (size_t)s, (int)sr); atomicAdd(acc + 2 * (size_t)s + 1, (int)si); }
+    }
+  } else {
+    for (uint32_t s = slot_lo + tid; s <= slot_hi; s += kT) {
+      const int lo = max((int)(g.begin(s) - tile_base), 0), hi = min((int)(g.end(s) - tile_base), t_hi);
+      uint32_t sr = 0, si = 0;
+      for (int o = lo; o < hi; ++o) {
+        const int2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
+        sr += (uint32_t)z.x; si += (uint32_t)z.y;
+      }
+      atomicAdd(acc + 2 * (size_t)s, (int)sr); atomicAdd(acc + 2 * (size_t)s + 1, (int)si);
     }
   }
 }
@@ -161,38 +201,134 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs 
   }
   __syncthreads();
 
-  // per-window partial sums of this tile
-  const uint32_t tile_lo = (uint32_t)tile_base;
-  const uint32_t tile_hi = (uint32_t)min((int64_t)a.n, tile_base + kTile);
-  if (tile_hi <= tile_lo) return;
-  WindowGrid g{a.ss, a.r0, a.first};
-  const uint32_t slot_lo = g.slot(tile_lo), slot_hi = g.slot(tile_hi - 1);
-  int *acc = (int *)a.acc_cur;
-  if (a.ss >= 16) {
-    for (uint32_t s = slot_lo + warp; s <= slot_hi; s += kT / 32) {
-      const int lo = (int)(max(g.begin(s), (int64_t)tile_lo) - tile_base);
-      const int hi = (int)(min(g.end(s), (int64_t)tile_hi) - tile_base);
-      uint32_t sr = 0, si = 0;
-      for (int o = lo + lane; o < hi; o += 32) {
-        const int2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
-        sr += (uint32_t)z.x; si += (uint32_t)z.y;
+  window_sums_int(a, zs, tile_base, tid);
+}
+
+// ---- integer kernel, compile-time tap count -------------------------------------------------------
+// Same arithmetic as above with the tap count LP fixed at compile time (taps zero-padded at the
+// FRONT to the next even count, which is exact): the tile is staged unpadded, every thread pulls
+// its LP+7 packed samples with 128-bit shared loads into registers ONCE, the taps sit in the
+// kernel's parameter (constant) bank so the FIR inner loop is nothing but IMADs with a constant
+// operand plus one unpack per sample -- no loads, no guards, no address arithmetic.
+struct IqbbTaps { int4 t[32]; };
+
+template <int LP, bool IS_S8>
+__global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccumArgs a, const __grid_constant__ IqbbTaps taps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = LP - 1;
+  constexpr int NV = (LP + 7 + 3) / 4;                 // 128-bit loads per thread
+  constexpr int n_xs = kTile + 4 * NV + 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int2 *lut = (int2 *)smem_raw;                                   // 128
+  int2 *zs = lut + 128;                                          // kR * kZRow
+  uint32_t *xs = (uint32_t *)(zs + kR * kZRow);                  // n_xs, 16-byte aligned
+
+  if (IS_S8) prologue<char2, int2>(a); else prologue<short2, int2>(a);
+
+  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+  if (tid < 128) lut[tid] = ((const int2 *)a.lut)[tid];
+  const int Hh = (int)a.hist_len;                                // history kept by the handle (= stripped taps - 1 <= H)
+  if (tile_base >= H && tile_base - H + n_xs <= (int64_t)a.n) {  // interior tile: no bounds, no history
+    if (IS_S8) {
+      const char2 *xg = (const char2 *)a.x + (tile_base - H);
+      for (int k = tid; k < n_xs; k += kT) {
+        const char2 s = xg[k];
+        xs[k] = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
       }
-      sr = __reduce_add_sync(kFull, sr);
-      si = __reduce_add_sync(kFull, si);
-      if (lane == 0) { atomicAdd(acc + 2 * (size_t)s, (int)sr); atomicAdd(acc + 2 * (size_t)s + 1, (int)si); }
+    } else {
+      const uint32_t *xg = (const uint32_t *)a.x + (tile_base - H);
+      for (int k = tid; k < n_xs; k += kT) xs[k] = xg[k];
     }
   } else {
-    for (uint32_t s = slot_lo + tid; s <= slot_hi; s += kT) {
-      const int lo = (int)(max(g.begin(s), (int64_t)tile_lo) - tile_base);
-      const int hi = (int)(min(g.end(s), (int64_t)tile_hi) - tile_base);
-      uint32_t sr = 0, si = 0;
-      for (int o = lo; o < hi; ++o) {
-        const int2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
-        sr += (uint32_t)z.x; si += (uint32_t)z.y;
+    for (int k = tid; k < n_xs; k += kT) {
+      const int64_t i = tile_base - H + k;
+      uint32_t v = 0;
+      if (IS_S8) {
+        char2 s = make_char2(0, 0);
+        if (i < 0) { if (Hh + i >= 0) s = ((const char2 *)a.hist_in)[Hh + i]; }
+        else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
+        v = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
+      } else {
+        if (i < 0) { if (Hh + i >= 0) v = ((const uint32_t *)a.hist_in)[Hh + i]; }
+        else if (i < (int64_t)a.n) v = ((const uint32_t *)a.x)[i];
       }
-      atomicAdd(acc + 2 * (size_t)s, (int)sr); atomicAdd(acc + 2 * (size_t)s + 1, (int)si);
+      xs[k] = v;
     }
   }
+  __syncthreads();
+
+  uint32_t w[4 * NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 q = ((const uint4 *)xs)[tid * 2 + v];
+    w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+  }
+  uint32_t A1[kR], A2[kR], A3[kR];
+  int wr[kR], wi[kR], ws[kR];
+#pragma unroll
+  for (int c = 0; c < kR; ++c) {
+    A1[c] = A2[c] = A3[c] = 0u;
+    unpack16(w[c], wr[c], wi[c]);
+    ws[c] = wr[c] + wi[c];
+  }
+#pragma unroll
+  for (int t = 0; t < LP; ++t) {
+    const int4 c = taps.t[t];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int s = (r + t) & (kR - 1);
+      A1[r] += (uint32_t)c.x * (uint32_t)ws[s];
+      A2[r] += (uint32_t)c.y * (uint32_t)wr[s];
+      A3[r] += (uint32_t)c.z * (uint32_t)wi[s];
+    }
+    if (t + 1 < LP) {
+      unpack16(w[t + kR], wr[t & (kR - 1)], wi[t & (kR - 1)]);
+      ws[t & (kR - 1)] = wr[t & (kR - 1)] + wi[t & (kR - 1)];
+    }
+  }
+
+  const int ob = tid * kR;
+  const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    int yr = ((int)(A1[r] - A3[r])) >> 14;
+    int yi = ((int)(A1[r] + A2[r])) >> 14;
+    if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }
+    if (a.nco) {
+      const uint32_t ph = (a.phase0 + (i0 + r) * a.inc) & 0x7fffu;
+      uint32_t idx = ph >> 8;
+      if (a.neg) idx = 127u - idx;
+      const int2 l = lut[idx];
+      const uint32_t pr = (uint32_t)l.x * (uint32_t)yr - (uint32_t)l.y * (uint32_t)yi;
+      const uint32_t pi = (uint32_t)l.x * (uint32_t)yi + (uint32_t)l.y * (uint32_t)yr;
+      if (IS_S8) { yr = (int)(short)(((int)(short)pr) >> 8); yi = (int)(short)(((int)(short)pi) >> 8); }
+      else { yr = ((int)pr) >> 16; yi = ((int)pi) >> 16; }
+    }
+    zs[r * kZRow + tid] = make_int2(yr, yi);
+  }
+  __syncthreads();
+
+  window_sums_int(a, zs, tile_base, tid);
+}
+
+template <int LP, bool IS_S8>
+int launch_fixed(const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned grid, cudaStream_t st) {
+  constexpr int NV = (LP + 7 + 3) / 4;
+  const size_t smem = sizeof(int2) * 128 + sizeof(int2) * kR * kZRow + sizeof(uint32_t) * (kTile + 4 * NV + 8);
+  iqbb_accum_int_fixed_kernel<LP, IS_S8><<<grid, kT, smem, st>>>(a, taps);
+  SDRG_CHECK_LAUNCH("iqbb_accum_int_fixed_kernel");
+  return SDRG_OK;
+}
+
+template <bool IS_S8>
+int dispatch_fixed(int lp, const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned grid, cudaStream_t st) {
+  switch (lp) {
+#define SDRG_CASE(N) case N: return launch_fixed<N, IS_S8>(a, taps, grid, st);
+    SDRG_CASE(2) SDRG_CASE(4) SDRG_CASE(6) SDRG_CASE(8) SDRG_CASE(10) SDRG_CASE(12) SDRG_CASE(14) SDRG_CASE(16)
+    SDRG_CASE(18) SDRG_CASE(20) SDRG_CASE(22) SDRG_CASE(24) SDRG_CASE(26) SDRG_CASE(28) SDRG_CASE(30) SDRG_CASE(32)
+#undef SDRG_CASE
+  }
+  return set_error(SDRG_ERR_RUNTIME, "no fixed-tap kernel for %d taps", lp);
 }
 
 // ---- float kernel (direct form; the folded fast path lives in iqbb_fold_kernels.cu) ---------------
@@ -322,6 +458,14 @@ size_t accum_smem_f32(uint32_t Lp, uint32_t H) {
 int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st) {
   if (a.n == 0) return SDRG_OK;
   const unsigned grid = (unsigned)((a.n + kTile - 1) / kTile);
+  if (scalar != SDRG_T_F32 && a.host_taps && a.taps_len <= 32) {
+    // zero taps in FRONT up to the next even count: x[n-(LP-1)+t] k'[t] with k'[t] = 0 for t < pad
+    const int lp = (int)((a.taps_len + 1) & ~1u), pad = lp - (int)a.taps_len;
+    IqbbTaps taps;
+    for (int t = 0; t < 32; ++t) taps.t[t] = make_int4(0, 0, 0, 0);
+    for (int t = 0; t < (int)a.taps_len; ++t) taps.t[pad + t] = ((const int4 *)a.host_taps)[t];
+    return scalar == SDRG_T_S8 ? dispatch_fixed<true>(lp, a, taps, grid, st) : dispatch_fixed<false>(lp, a, taps, grid, st);
+  }
   if (scalar == SDRG_T_F32) {
     const size_t smem = accum_smem_f32(a.taps_len, a.hist_len);
     if (smem > 48 * 1024)

@@ -14,7 +14,8 @@ struct IqbbAccumArgs {
   const void *x;          // n input samples (char2 / short2 / float2), device
   const void *hist_in;    // the previous `hist_len` samples (same type), device
   void       *hist_out;   // receives the last `hist_len` samples of [hist_in | x]
-  const void *taps;       // int: 3 x Lp int32 (Gauss form, see iqbb_kernels.cu); float: Lp float2
+  const void *taps;       // int: Lp x int4 (Gauss form, see iqbb_kernels.cu); float: Lp float2
+  const void *host_taps;  // the same int4 taps in host memory (enables the fixed-tap-count kernels), or null
   const void *lut;        // 128 x int2 or 128 x float2
   void       *acc_cur;    // window accumulators of this call (int2 / float2), slot 0 = open window
   void       *acc_next;   // accumulators of the next call: zeroed here (first `zero_next` entries)
