@@ -146,6 +146,168 @@ __global__ void __launch_bounds__(kT) bank_accum_kernel(const BankAccumArgs a) {
   }
 }
 
+// ---- compile-time tap count ---------------------------------------------------------------------------
+// As in iqbb_accum_int_fixed_kernel: the tile is staged unpadded, every thread pulls its LP+7 packed
+// samples into registers ONCE (128-bit shared loads) and keeps them for ALL channels of the group;
+// the channel loop then consists of broadcast tap loads, one unpack per tap step and IMADs.
+template <int LP, bool IS_S8>
+__global__ void __launch_bounds__(kT) bank_accum_fixed_kernel(const BankAccumArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = LP - 1;
+  constexpr int NV = (LP + 7 + 3) / 4;
+  constexpr int n_xs = kTile + 4 * NV + 8;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int Ls = (int)a.taps_len, pad = LP - Ls;                 // stored taps per channel; zero taps in front
+  const int c0 = blockIdx.y * a.group;
+  const int nch = min((int)a.group, (int)a.channels - c0);
+  uint32_t *xs = (uint32_t *)smem_raw;                           // n_xs (16-byte aligned)
+  int4 *tp = (int4 *)(xs + ((n_xs + 3) & ~3));                   // group x LP
+  int2 *lut = (int2 *)(tp + (size_t)a.group * LP);               // 128
+
+  {
+    int2 *nxt = (int2 *)a.acc_next;
+    const size_t total = (size_t)a.zero_next * a.channels;
+    const size_t stride = (size_t)gridDim.x * gridDim.y * blockDim.x;
+    for (size_t k = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + tid; k < total; k += stride)
+      nxt[(k / a.zero_next) * a.acc_stride + (k % a.zero_next)] = make_int2(0, 0);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      const int64_t n = a.n, Hh = a.hist_len;
+      for (int64_t k = tid; k < Hh; k += blockDim.x) {
+        const int64_t i = n - Hh + k;
+        if (IS_S8) ((char2 *)a.hist_out)[k] = (i >= 0) ? ((const char2 *)a.x)[i] : ((const char2 *)a.hist_in)[Hh + i];
+        else ((uint32_t *)a.hist_out)[k] = (i >= 0) ? ((const uint32_t *)a.x)[i] : ((const uint32_t *)a.hist_in)[Hh + i];
+      }
+    }
+  }
+
+  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
+  for (int k = tid; k < nch * LP; k += kT) {
+    const int ch = k / LP, t = k - ch * LP;
+    tp[k] = t < pad ? make_int4(0, 0, 0, 0) : ((const int4 *)a.taps)[(size_t)(c0 + ch) * Ls + (t - pad)];
+  }
+  if (tid < 128) lut[tid] = ((const int2 *)a.lut)[tid];
+  const int Hh = (int)a.hist_len;
+  for (int k = tid; k < n_xs; k += kT) {
+    const int64_t i = tile_base - H + k;
+    uint32_t v = 0;
+    if (IS_S8) {
+      char2 s = make_char2(0, 0);
+      if (i < 0) { if (Hh + i >= 0) s = ((const char2 *)a.hist_in)[Hh + i]; }
+      else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
+      v = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
+    } else {
+      if (i < 0) { if (Hh + i >= 0) v = ((const uint32_t *)a.hist_in)[Hh + i]; }
+      else if (i < (int64_t)a.n) v = ((const uint32_t *)a.x)[i];
+    }
+    xs[k] = v;
+  }
+  __syncthreads();
+
+  uint32_t w[4 * NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 q = ((const uint4 *)xs)[tid * 2 + v];
+    w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+  }
+
+  const int ob = tid * kR;
+  const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
+  const uint32_t tile_hi = (uint32_t)min((int64_t)a.n, tile_base + kTile);
+  const uint32_t q0 = a.r0 + i0 - ((a.first && i0 > 0) ? 1u : 0u);
+  const uint32_t slot_a = q0 / a.ss;
+  const uint32_t bnd = (slot_a + 1) * a.ss - a.r0 + a.first;      // first index of slot_a + 1
+  const uint32_t w_i0 = (uint32_t)tile_base + (uint32_t)((tid & ~31) * kR);
+  const uint32_t slot_w = (a.r0 + w_i0 - ((a.first && w_i0 > 0) ? 1u : 0u)) / a.ss;
+  // which of this thread's 8 outputs go to the upper of the warp's two windows (bit r), and which exist
+  uint32_t upper_mask = 0, valid_mask = 0;
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const uint32_t i = i0 + r;
+    const bool up = (i >= bnd) ? (slot_a + 1 != slot_w) : (slot_a != slot_w);
+    upper_mask |= (up ? 1u : 0u) << r;
+    valid_mask |= ((i < tile_hi) ? 1u : 0u) << r;
+  }
+
+  for (int ch = 0; ch < nch; ++ch) {
+    const int c = c0 + ch;
+    const int4 *tpc = tp + ch * LP;
+    uint32_t A1[kR], A2[kR], A3[kR];
+    int wr[kR], wi[kR], ws[kR];
+#pragma unroll
+    for (int k = 0; k < kR; ++k) {
+      A1[k] = A2[k] = A3[k] = 0u;
+      unpack16(w[k], wr[k], wi[k]);
+      ws[k] = wr[k] + wi[k];
+    }
+#pragma unroll
+    for (int t = 0; t < LP; ++t) {
+      const int4 cf = tpc[t];
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const int s = (r + t) & (kR - 1);
+        A1[r] += (uint32_t)cf.x * (uint32_t)ws[s];
+        A2[r] += (uint32_t)cf.y * (uint32_t)wr[s];
+        A3[r] += (uint32_t)cf.z * (uint32_t)wi[s];
+      }
+      if (t + 1 < LP) {
+        unpack16(w[t + kR], wr[t & (kR - 1)], wi[t & (kR - 1)]);
+        ws[t & (kR - 1)] = wr[t & (kR - 1)] + wi[t & (kR - 1)];
+      }
+    }
+    const uint32_t inc = a.inc[c] & 0x7fffu;
+    const bool nco = a.inc[c] != 0;
+    const uint32_t negx = a.neg[c] ? 127u : 0u;                  // idx = 127 - idx  <=>  idx ^ 127 for idx in 0..127
+    uint32_t ph = (a.consumed15 * inc + i0 * inc) & 0x7fffu;
+    uint32_t lo_r = 0, lo_i = 0, hi_r = 0, hi_i = 0;
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      int yr = ((int)(A1[r] - A3[r])) >> 14;
+      int yi = ((int)(A1[r] + A2[r])) >> 14;
+      if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }
+      if (nco) {
+        const int2 l = lut[(ph >> 8) ^ negx];
+        ph = (ph + inc) & 0x7fffu;
+        const uint32_t pr = (uint32_t)l.x * (uint32_t)yr - (uint32_t)l.y * (uint32_t)yi;
+        const uint32_t pi = (uint32_t)l.x * (uint32_t)yi + (uint32_t)l.y * (uint32_t)yr;
+        if (IS_S8) { yr = (int)(short)(((int)(short)pr) >> 8); yi = (int)(short)(((int)(short)pi) >> 8); }
+        else { yr = ((int)pr) >> 16; yi = ((int)pi) >> 16; }
+      }
+      if ((valid_mask >> r) & 1u) {
+        if ((upper_mask >> r) & 1u) { hi_r += (uint32_t)yr; hi_i += (uint32_t)yi; } else { lo_r += (uint32_t)yr; lo_i += (uint32_t)yi; }
+      }
+    }
+    lo_r = __reduce_add_sync(kFull, lo_r); lo_i = __reduce_add_sync(kFull, lo_i);
+    hi_r = __reduce_add_sync(kFull, hi_r); hi_i = __reduce_add_sync(kFull, hi_i);
+    if (lane == 0) {
+      int *acc = (int *)a.acc_cur + 2 * ((size_t)c * a.acc_stride + slot_w);
+      if (lo_r | lo_i) { atomicAdd(acc, (int)lo_r); atomicAdd(acc + 1, (int)lo_i); }
+      if (hi_r | hi_i) { atomicAdd(acc + 2, (int)hi_r); atomicAdd(acc + 3, (int)hi_i); }
+    }
+  }
+}
+
+template <int LP, bool IS_S8>
+int launch_bank_fixed(const BankAccumArgs &a, dim3 grid, cudaStream_t st) {
+  constexpr int NV = (LP + 7 + 3) / 4;
+  constexpr int n_xs = kTile + 4 * NV + 8;
+  const size_t smem = sizeof(uint32_t) * ((n_xs + 3) & ~3) + sizeof(int4) * (size_t)a.group * LP + sizeof(int2) * 128;
+  if (smem > 48 * 1024) SDRG_CUDA(cudaFuncSetAttribute(bank_accum_fixed_kernel<LP, IS_S8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bank_accum_fixed_kernel<LP, IS_S8><<<grid, kT, smem, st>>>(a);
+  SDRG_CHECK_LAUNCH("bank_accum_fixed_kernel");
+  return SDRG_OK;
+}
+
+template <bool IS_S8>
+int dispatch_bank_fixed(int lp, const BankAccumArgs &a, dim3 grid, cudaStream_t st) {
+  switch (lp) {
+#define SDRG_CASE(N) case N: return launch_bank_fixed<N, IS_S8>(a, grid, st);
+    SDRG_CASE(2) SDRG_CASE(4) SDRG_CASE(6) SDRG_CASE(8) SDRG_CASE(10) SDRG_CASE(12) SDRG_CASE(14) SDRG_CASE(16)
+    SDRG_CASE(18) SDRG_CASE(20) SDRG_CASE(22) SDRG_CASE(24) SDRG_CASE(26) SDRG_CASE(28) SDRG_CASE(30) SDRG_CASE(32)
+#undef SDRG_CASE
+  }
+  return set_error(SDRG_ERR_RUNTIME, "no fixed-tap bank kernel for %d taps", lp);
+}
+
 // finalize for every channel: blockIdx.y = channel
 template <int SCALAR>
 __global__ void __launch_bounds__(256) bank_finalize_kernel(const IqbbFinalizeArgs base, const BankFinalizeStrides s) {
@@ -170,6 +332,10 @@ int launch_bank_accum(int scalar, const BankAccumArgs &a, cudaStream_t st) {
   const size_t smem = sizeof(int4) * (size_t)a.group * a.taps_len + sizeof(int2) * 128 + sizeof(uint32_t) * (n_xs + (n_xs >> 5) + 1);
   if (smem > 200 * 1024) return set_error(SDRG_ERR_RUNTIME, "bank: filter order too large for the bank kernel");
   dim3 grid((unsigned)((a.n + kTile - 1) / kTile), (unsigned)((a.channels + a.group - 1) / a.group));
+  if (a.taps_len <= 32) {
+    const int lp = (int)((a.taps_len + 1) & ~1u);
+    return scalar == SDRG_T_S8 ? dispatch_bank_fixed<true>(lp, a, grid, st) : dispatch_bank_fixed<false>(lp, a, grid, st);
+  }
   if (scalar == SDRG_T_S8) {
     if (smem > 48 * 1024) SDRG_CUDA(cudaFuncSetAttribute(bank_accum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bank_accum_kernel<true><<<grid, kT, smem, st>>>(a);
