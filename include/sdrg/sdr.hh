@@ -10,4 +10,6 @@
 #include "node.hh"
 #include "baseband.hh"
 #include "demod.hh"
+#include "fftplan.hh"
+#include "filternode.hh"
 #endif

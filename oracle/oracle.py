@@ -177,6 +177,34 @@ def usbdemod(x, scalar):
     return out
 
 
+_lib.orc_autocast_u8_s16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+_lib.orc_autocast_s8_s16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+_lib.orc_fmdeemph_alpha.argtypes = [C.c_double]
+_lib.orc_fmdeemph_alpha.restype = C.c_int
+_lib.orc_fmdeemph_s16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+
+
+def autocast_cs16(x):
+    """AutoCast<complex<int16>> of complex uint8 / int8 input (n,2) -> (n,2) int16."""
+    x = np.ascontiguousarray(x)
+    out = np.zeros(x.shape, dtype=np.int16)
+    fn = _lib.orc_autocast_u8_s16 if x.dtype == np.uint8 else _lib.orc_autocast_s8_s16
+    fn(_p(x), x.size, _p(out))
+    return out
+
+
+class FMDeemph:
+    def __init__(self, sample_rate):
+        self.alpha = int(_lib.orc_fmdeemph_alpha(float(sample_rate)))
+        self.avg = np.zeros(1, dtype=np.int16)
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        out = np.zeros_like(x)
+        _lib.orc_fmdeemph_s16(_p(x), x.size, _p(out), self.alpha, _p(self.avg))
+        return out
+
+
 def fast_atan2_i32(a, b):
     return int(_lib.orc_fast_atan2_i32(int(a), int(b)))
 

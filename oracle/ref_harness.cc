@@ -12,6 +12,10 @@
 //   ola <in.bin cf32> <block> <Fs> <fmin> <fmax> <prefix>
 //         runs FilterSink<float> -> FilterSource<float> with a double-precision FFTPlan stand-in
 //         (FFTW3 is not installed); writes <prefix>.kern/.taps/.out
+//   cast <cu8|cs8> <in.bin> <buffer_size> <prefix>
+//         runs AutoCast< std::complex<int16_t> > on complex 8-bit input; writes <prefix>.cs16
+//   deemph <in.bin int16> <buffer_size> <Fs> <prefix>
+//         runs FMDeemph<int16_t> (in place and out of place give the same samples); writes <prefix>.out
 //   time <s16|s8> <in.bin> <buffer_size> <Fs> <Fc> <Ff> <width> <order> <sub_sample> <oFs> <threads> <min_seconds>
 //         times IQBaseBand<T> -> FMDemod, in place, direct connections, T independent chains;
 //         prints one JSON line with input Msamples/s
@@ -57,6 +61,7 @@ protected:
 #include "baseband.hh"
 #include "demod.hh"
 #include "filternode.hh"
+#include "autocast.hh"
 
 using namespace sdr;
 
@@ -230,6 +235,46 @@ static int run_ola(char **a) {
   return 0;
 }
 
+template <class T>
+static int run_cast(char **a) {
+  std::vector<char> raw = slurp(a[0]);
+  size_t bs = strtoull(a[1], 0, 10);
+  std::string prefix = a[2];
+  size_t total = raw.size() / sizeof(T);
+  Feed<T> feed; AutoCast< std::complex<int16_t> > cast; Dump< std::complex<int16_t> > dump;
+  dump.f = wopen(prefix + ".cs16");
+  feed.connect(&cast, true); cast.connect(&dump, true);
+  feed.setup(1e6, bs);
+  Buffer<T> work(bs);
+  for (size_t off = 0; off < total; off += bs) {
+    size_t n = std::min(bs, total - off);
+    memcpy(work.data(), raw.data() + off * sizeof(T), n * sizeof(T));
+    feed.push(work.head(n), false);
+  }
+  fclose(dump.f);
+  return 0;
+}
+
+static int run_deemph(char **a) {
+  std::vector<char> raw = slurp(a[0]);
+  size_t bs = strtoull(a[1], 0, 10);
+  double Fs = atof(a[2]);
+  std::string prefix = a[3];
+  size_t total = raw.size() / sizeof(int16_t);
+  Feed<int16_t> feed; FMDeemph<int16_t> de; Dump<int16_t> dump;
+  dump.f = wopen(prefix + ".out");
+  feed.connect(&de, true); de.connect(&dump, true);
+  feed.setup(Fs, bs);
+  Buffer<int16_t> work(bs);
+  for (size_t off = 0; off < total; off += bs) {
+    size_t n = std::min(bs, total - off);
+    memcpy(work.data(), raw.data() + off * sizeof(int16_t), n * sizeof(int16_t));
+    feed.push(work.head(n), true);
+  }
+  fclose(dump.f);
+  return 0;
+}
+
 template <class T> class Null : public Sink<T> {
 public:
   Null() : n(0), acc(0) {}
@@ -299,6 +344,11 @@ int main(int argc, char **argv) {
       if (!strcmp(argv[2], "s8")) return run_bb<int8_t, int16_t>(argv + 3);
     } else if (cmd == "ola" && argc == 8) {
       return run_ola(argv + 2);
+    } else if (cmd == "cast" && argc == 6) {
+      if (!strcmp(argv[2], "cu8")) return run_cast< std::complex<uint8_t> >(argv + 3);
+      if (!strcmp(argv[2], "cs8")) return run_cast< std::complex<int8_t> >(argv + 3);
+    } else if (cmd == "deemph" && argc == 6) {
+      return run_deemph(argv + 2);
     } else if (cmd == "time" && argc == 14) {
       if (!strcmp(argv[2], "s16")) return run_time<int16_t, int16_t>(argv + 3);
       if (!strcmp(argv[2], "s8")) return run_time<int8_t, int16_t>(argv + 3);

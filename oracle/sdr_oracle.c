@@ -333,6 +333,24 @@ void orc_usbdemod_f32(const float *in, size_t n, float *out) {
   for (size_t i = 0; i < n; i++) out[i] = (in[2 * i] + in[2 * i + 1]) / 2;
 }
 
+/* ---- AutoCast (src/autocast.hh:187-204) and FMDeemph (src/demod.hh:271-362) ------------------- */
+void orc_autocast_u8_s16(const uint8_t *in, size_t n, int16_t *out) {
+  const int8_t *v = (const int8_t *)in;           /* the reference reads uint8 data through int8_t* */
+  for (size_t i = 0; i < n; i++) out[i] = (int16_t)(((int)(int16_t)v[i] - 127) << 8);
+}
+void orc_autocast_s8_s16(const int8_t *in, size_t n, int16_t *out) {
+  for (size_t i = 0; i < n; i++) out[i] = (int16_t)((int)(int16_t)in[i] << 8);
+}
+int orc_fmdeemph_alpha(double Fs) { return (int)round(1.0 / ((1.0 - exp(-1.0 / (Fs * 75e-6))))); }
+void orc_fmdeemph_s16(const int16_t *in, size_t n, int16_t *out, int alpha, int16_t *avg) {
+  for (size_t i = 0; i < n; i++) {
+    int16_t diff = (int16_t)(in[i] - *avg);       /* Scalar diff = in[i] - _avg */
+    if (diff > 0) *avg = (int16_t)(*avg + (diff + alpha / 2) / alpha);
+    else *avg = (int16_t)(*avg + (diff - alpha / 2) / alpha);
+    out[i] = *avg;
+  }
+}
+
 /* ---- FFT stand-in ---------------------------------------------------------------------------- */
 
 static int is_pow2(size_t n) { return n && !(n & (n - 1)); }

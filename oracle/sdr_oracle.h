@@ -82,6 +82,16 @@ void orc_usbdemod_s16(const int16_t *in_iq, size_t n, int16_t *out);
 void orc_usbdemod_s8(const int8_t *in_iq, size_t n, int8_t *out);
 void orc_usbdemod_f32(const float *in_iq, size_t n, float *out);
 
+/* AutoCast< std::complex<int16_t> > from complex 8-bit input (src/autocast.hh:187-204): n BYTES in,
+ * n int16 out.  cu8: the bytes are read through an int8_t pointer (reference quirk), (v-127)<<8;
+ * cs8: v<<8. */
+void orc_autocast_u8_s16(const uint8_t *in, size_t n_bytes, int16_t *out);
+void orc_autocast_s8_s16(const int8_t *in, size_t n_bytes, int16_t *out);
+/* FMDeemph<int16_t> (src/demod.hh:271-362): alpha = round(1/(1-exp(-1/(Fs*75e-6)))); the running
+ * average `avg` (int16) is carried by the caller and reset to 0 by config(). */
+int  orc_fmdeemph_alpha(double sample_rate);
+void orc_fmdeemph_s16(const int16_t *in, size_t n, int16_t *out, int alpha, int16_t *avg);
+
 /* FFT (stand-in for the un-vendored FFTW3 behind src/fftplan_fftw3.hh:79-142): unnormalised DFT,
  * dir=+1 forward exp(-i..), dir=-1 backward exp(+i..). Power-of-two n: iterative radix-2 in double;
  * otherwise O(n^2) DFT in double. Interleaved re,im. */

@@ -79,6 +79,26 @@ def main():
                 am=np.fromfile(pre + ".am", dtype=dt),
                 usb=np.fromfile(pre + ".usb", dtype=dt))
             print("wrote", name, "ss=%d inc=%d outputs=%d" % (hdr[1], hdr[2], np.fromfile(pre + ".counts", dtype=np.uint32).sum()))
+        # AutoCast<complex<int16>> from cu8 / cs8, and FMDeemph<int16> (the nodes either side of the path)
+        g = np.random.Generator(np.random.MT19937(0x5D12000A))
+        for fmt, dt in (("cu8", np.uint8), ("cs8", np.int8)):
+            x = g.integers(np.iinfo(dt).min, np.iinfo(dt).max + 1, size=(5000, 2)).astype(dt)
+            x[:4] = [[0, 255], [127, 128], [1, 254], [126, 129]] if dt == np.uint8 else [[-128, 127], [0, -1], [1, -127], [126, -126]]
+            inp = os.path.join(td, "cast_" + fmt + ".in"); x.tofile(inp)
+            pre = os.path.join(td, "cast_" + fmt)
+            run(["cast", fmt, inp, 1024, pre])
+            np.savez_compressed(os.path.join(HERE, "cast_" + fmt + ".npz"), x=x,
+                                out=np.fromfile(pre + ".cs16", dtype=np.int16).reshape(-1, 2))
+            print("wrote cast_" + fmt)
+        for name, Fs in (("deemph_48k", 48000.0), ("deemph_8k", 8000.0), ("deemph_200k", 200e3)):
+            x = (8000 * np.sin(2 * np.pi * 1e3 * np.arange(6000) / Fs)).astype(np.int16) + g.integers(-3000, 3001, size=6000).astype(np.int16)
+            x[100:110] = [32767, -32768, 32767, -32768, 0, 1, -1, 2, -2, 32767]
+            inp = os.path.join(td, name + ".in"); x.tofile(inp)
+            pre = os.path.join(td, name)
+            run(["deemph", inp, 1000, repr(Fs), pre])
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, Fs=Fs, buffer_size=1000,
+                                out=np.fromfile(pre + ".out", dtype=np.int16))
+            print("wrote", name)
         for (name, block, Fs, fmin, fmax, nblk) in OLA_CASES:
             x = synth.iq_f32(block * nblk, Fs, [(0.5, 200e3, 0.0), (0.25, 1.5e6, 0.5), (0.1667, -3e6, 1.0)], 0.01, 0x5D120003)
             inp = os.path.join(td, name + ".in"); x.tofile(inp)

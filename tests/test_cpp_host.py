@@ -31,7 +31,7 @@ def test_buffer_and_node_conformance():
 def test_compat_headers_compile_reference_style_source(tmp_path):
     """A source file written against libsdr's own header names builds unchanged with the compat dir."""
     src = tmp_path / "ref_style.cc"
-    src.write_text('#include "demod.hh"\n#include "baseband.hh"\n#include "queue.hh"\nusing namespace sdr;\n'
+    src.write_text('#include "demod.hh"\n#include "baseband.hh"\n#include "queue.hh"\n#include "filternode.hh"\n#include "fftplan.hh"\nusing namespace sdr;\n'
                    "int main() { IQBaseBand<int16_t> *bb = 0; FMDemod<int16_t> *d = 0; (void)bb; (void)d; return 0; }\n")
     subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include", "sdrg", "compat"),
                     "-I" + os.path.join(ROOT, "include"), str(src)], check=True, capture_output=True, text=True)
@@ -46,3 +46,14 @@ def test_sdr_fm_shaped_chain_bit_exact():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "chain_test: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_filternode_and_fftplan_classes():
+    os.makedirs(BUILD, exist_ok=True)
+    obj = os.path.join(BUILD, "sdr_oracle.o")
+    subprocess.run(["gcc", "-O2", "-fwrapv", "-c", os.path.join(ROOT, "oracle", "sdr_oracle.c"), "-o", obj], check=True)
+    exe = compile_cpp("filter_test", extra=[obj])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "filter_test: ok" in r.stdout

@@ -110,3 +110,18 @@ def test_fft_stand_in_against_numpy():
         x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
         assert rel_rms(orc.fft_f64(x, +1), np.fft.fft(x)) < 1e-13
         assert rel_rms(orc.fft_f64(x, -1), np.fft.ifft(x) * n) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["cast_cu8", "cast_cs8"])
+def test_autocast_matches_reference(name):
+    g = load_golden(name)
+    np.testing.assert_array_equal(orc.autocast_cs16(g["x"]), g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names("deemph_"))
+def test_fmdeemph_matches_reference(name):
+    g = load_golden(name)
+    d = orc.FMDeemph(float(g["Fs"]))
+    bs = int(g["buffer_size"])
+    out = np.concatenate([d.process(g["x"][o:o + bs]) for o in range(0, g["x"].shape[0], bs)])
+    np.testing.assert_array_equal(out, g["out"])
