@@ -105,6 +105,12 @@ int sdrg_iqbb_configure(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out);
  * (sdrg_iqbb_get_info) on a machine without a GPU. */
 int sdrg_iqbb_design(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out);
 
+/* AutoCast fused into the load (examples/sdr_fm.cc:39,49-50 put AutoCast< complex<int16_t> > in front
+ * of IQBaseBand<int16_t>): with type SDRG_T_CU8 or SDRG_T_CS8 an int16 node consumes the raw complex
+ * 8-bit stream and converts on the fly exactly like src/autocast.hh:187-204 (2 bytes per sample from
+ * HBM instead of 4, no separate pass).  Call before config(); config() then expects that type. */
+int sdrg_iqbb_set_input_type(sdrg_iqbb *h, int type);
+
 /* SDRG_T_F32 only: which accumulate kernel config() selects.  0 = auto (folded when
  * sub_sample >= max(32, order-1), else direct), 1 = direct (sample-by-sample FIR, FMA-bound),
  * 2 = folded (one weight per input sample, HBM-bound; SDRG_ERR_CONFIG at config() if not eligible),
@@ -155,6 +161,21 @@ int sdrg_amdemod_process(int scalar, const void *in, size_t n, void *out);
 int sdrg_amdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream);
 int sdrg_usbdemod_process(int scalar, const void *in, size_t n, void *out);
 int sdrg_usbdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream);
+
+/* ---- the nodes either side of the path ------------------------------------------
+ * AutoCast< std::complex<int16_t> > from complex uint8 / int8 (src/autocast.hh:187-204); n complex
+ * samples.  Other casts: SDRG_ERR_CONFIG with the reference's message. */
+int sdrg_autocast_process(int in_type, int out_type, const void *in, size_t n, void *out);
+int sdrg_autocast_process_dev(int in_type, int out_type, const void *d_in, size_t n, void *d_out, void *stream);
+/* FMDeemph<int16_t> (src/demod.hh:271-362): integer 1-pole IIR with rounding.  `streams` independent
+ * sequences (e.g. the channels of a bank), each n samples long, `stride` elements apart; the running
+ * average of every stream is carried across calls and reset by configure(). */
+typedef struct sdrg_fmdeemph sdrg_fmdeemph;
+int sdrg_fmdeemph_create(size_t streams, sdrg_fmdeemph **h);
+int sdrg_fmdeemph_destroy(sdrg_fmdeemph *h);
+int sdrg_fmdeemph_configure(sdrg_fmdeemph *h, const sdrg_config *src, sdrg_config *out);
+int sdrg_fmdeemph_process(sdrg_fmdeemph *h, const void *in, size_t n, size_t stride, void *out);
+int sdrg_fmdeemph_process_dev(sdrg_fmdeemph *h, const void *d_in, size_t n, size_t stride, void *d_out, void *stream);
 
 /* ---- receive chain: IQBaseBand -> demod, many buffers per launch ------------------------------
  * Equivalent to n_buffers consecutive Source::send() calls of buffer_size samples each through

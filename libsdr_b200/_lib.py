@@ -79,6 +79,14 @@ SIGNATURES = {
     "sdrg_iqbb_set_output_sample_rate": [_V, _D],
     "sdrg_iqbb_configure": [_V, _PCFG, _PCFG],
     "sdrg_iqbb_set_float_path": [_V, _I],
+    "sdrg_iqbb_set_input_type": [_V, _I],
+    "sdrg_autocast_process": [_I, _I, _V, _SZ, _V],
+    "sdrg_autocast_process_dev": [_I, _I, _V, _SZ, _V, _V],
+    "sdrg_fmdeemph_create": [_SZ, _PV],
+    "sdrg_fmdeemph_destroy": [_V],
+    "sdrg_fmdeemph_configure": [_V, _PCFG, _PCFG],
+    "sdrg_fmdeemph_process": [_V, _V, _SZ, _SZ, _V],
+    "sdrg_fmdeemph_process_dev": [_V, _V, _SZ, _SZ, _V, _V],
     "sdrg_iqbb_design": [_V, _PCFG, _PCFG],
     "sdrg_iqbb_get_info": [_V, C.POINTER(IqbbInfo), _V, _V],
     "sdrg_iqbb_process": [_V, _V, _SZ, _V, _SZ, _PSZ],

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -104,6 +105,7 @@ struct sdrg_iqbb {
   uint32_t taps_len = 1, hist_len = 0;
   std::vector<int32_t> host_taps;      // int paths: the Gauss-form taps as uploaded
   // folded float path (iqbb_fold_kernels.cu)
+  int in_fmt = 0;                      // int16 only: 0 native, 2 complex uint8, 3 complex int8 (fused AutoCast)
   int float_path = 0;                  // 0 auto, 1 direct, 2 folded
   bool fold = false;
   void *d_tab_a = nullptr, *d_tab_u = nullptr;
@@ -139,12 +141,16 @@ struct sdrg_rxchain {
 namespace {
 
 size_t sample_bytes(int scalar) { return 2 * scalar_bytes(scalar); }
+size_t in_sample_bytes(const sdrg_iqbb *h);   // bytes per INPUT sample (2 when AutoCast is fused into the load)
 size_t acc_bytes() { return 8; }   // int2 / float2
 
 size_t audio_bytes(int scalar, int demod) {
   if (demod == SDRG_DEMOD_FM) return scalar == SDRG_T_F32 ? 4 : 2;
   return scalar_bytes(scalar);
 }
+
+size_t in_sample_bytes(const sdrg_iqbb *h) { return h->in_fmt ? 2 : sample_bytes(h->d.scalar); }
+int input_type_of(const sdrg_iqbb *h) { return h->in_fmt == 2 ? SDRG_T_CU8 : (h->in_fmt == 3 ? SDRG_T_CS8 : complex_type_of(h->d.scalar)); }
 
 int grow(void **p, size_t *cap, size_t need) {
   if (*cap >= need && *p) return SDRG_OK;
@@ -241,10 +247,11 @@ int upload_design(sdrg_iqbb *h) {
   int rc_fold = upload_fold_tables(h);
   if (rc_fold) return rc_fold;
   h->hist_len = h->taps_len - 1;
-  const size_t hb = (h->hist_len ? h->hist_len : 1) * sample_bytes(d.scalar);
+  const size_t hb = (h->hist_len ? h->hist_len : 1) * sample_bytes(d.scalar);   // >= the fused-AutoCast element size
   for (int k = 0; k < 2; ++k) {
     SDRG_CUDA(cudaMalloc(&h->d_hist[k], hb));
-    SDRG_CUDA(cudaMemset(h->d_hist[k], 0, hb));     // ring zeroed in the ctor (baseband.hh:42-43)
+    // ring zeroed in the ctor (baseband.hh:42-43); a zero sample in cu8 form is the byte 127
+    SDRG_CUDA(cudaMemset(h->d_hist[k], h->in_fmt == 2 ? 127 : 0, hb));
   }
   return SDRG_OK;
 }
@@ -327,6 +334,7 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   a.phase0 = h->phase0; a.inc = (uint32_t)(h->d.lut_inc & 0x7fffu); a.nco = h->d.lut_inc != 0 ? 1u : 0u;
   a.neg = h->d.negative ? 1u : 0u;
   a.zero_next = h->acc_dirty[q];
+  a.in_fmt = (uint32_t)h->in_fmt;
   IqbbFinalizeArgs f{};
   f.acc_cur = h->d_acc[p]; f.acc_next = h->d_acc[q];
   f.bb_out = d_bb; f.audio_out = d_audio;
@@ -695,6 +703,17 @@ int sdrg_iqbb_set_output_sample_rate(sdrg_iqbb *h, double oFs) {
   return reconfigure(h);
 }
 
+int sdrg_iqbb_set_input_type(sdrg_iqbb *h, int type) {
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: select the input type before config()");
+  if (type == complex_type_of(h->d.scalar)) { h->in_fmt = 0; return SDRG_OK; }
+  if (h->d.scalar != SDRG_T_S16 || (type != SDRG_T_CU8 && type != SDRG_T_CS8))
+    return set_error(SDRG_ERR_CONFIG, "AutoCast: Can not cast from type %s (%d) to %s (%d)", type_name(type), type,
+                     type_name(complex_type_of(h->d.scalar)), complex_type_of(h->d.scalar));
+  h->in_fmt = type == SDRG_T_CU8 ? 2 : 3;
+  return SDRG_OK;
+}
+
 int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (mode < 0 || mode > 3) return set_error(SDRG_ERR_ARG, "IQBaseBand: float path must be 0 (auto), 1 (direct), 2 (folded) or 3 (folded, TMA staging)");
@@ -707,7 +726,7 @@ int sdrg_iqbb_configure(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out) 
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
   bool skip = false;
-  int rc = config_common("IQBaseBand", complex_type_of(h->d.scalar), src, true, &skip);
+  int rc = config_common("IQBaseBand", input_type_of(h), src, true, &skip);
   if (rc || skip) return rc;
   SDRG_CUDA(cudaSetDevice(h->device));
   SDRG_CUDA(cudaDeviceSynchronize());
@@ -728,7 +747,7 @@ int sdrg_iqbb_design(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
   bool skip = false;
-  int rc = config_common("IQBaseBand", complex_type_of(h->d.scalar), src, true, &skip);
+  int rc = config_common("IQBaseBand", input_type_of(h), src, true, &skip);
   if (rc || skip) return rc;
   h->d.Fs = int32_t(src->sample_rate);
   h->d.source_bs = src->buffer_size;
@@ -780,12 +799,12 @@ int sdrg_iqbb_process_dev(sdrg_iqbb *h, const void *d_in, size_t n_in, void *d_o
   const size_t total = (size_t)advance(h, n_in).n_out;
   if (total > out_cap) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: output buffer too small (%zu < %zu)", out_cap, total);
   SDRG_CUDA(cudaSetDevice(h->device));
-  const size_t sb = sample_bytes(h->d.scalar);
+  const size_t sb = sample_bytes(h->d.scalar), isb = in_sample_bytes(h);
   size_t done = 0, produced = 0;
   while (done < n_in) {
     const uint32_t n = (uint32_t)((n_in - done) > (1u << 30) ? (1u << 30) : (n_in - done));
     uint64_t got = 0;
-    rc = run_call(h, (const char *)d_in + done * sb, n, (char *)d_out + produced * sb, nullptr, SDRG_DEMOD_NONE, 0, 0,
+    rc = run_call(h, (const char *)d_in + done * isb, n, (char *)d_out + produced * sb, nullptr, SDRG_DEMOD_NONE, 0, 0,
                   nullptr, nullptr, (cudaStream_t)stream, &got);
     if (rc) return rc;
     done += n; produced += got;
@@ -809,9 +828,10 @@ int sdrg_iqbb_process(sdrg_iqbb *h, const void *in, size_t n_in, void *out, size
   const size_t sb = sample_bytes(h->d.scalar);
   const size_t total = (size_t)advance(h, n_in).n_out;
   if (total > out_cap) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: output buffer too small (%zu < %zu)", out_cap, total);
-  if ((rc = grow(&h->d_in, &h->in_cap, n_in * sb))) return rc;
+  const size_t isb = in_sample_bytes(h);
+  if ((rc = grow(&h->d_in, &h->in_cap, n_in * isb))) return rc;
   if ((rc = grow(&h->d_out, &h->out_cap, (total + 1) * sb))) return rc;
-  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n_in * sb, cudaMemcpyHostToDevice, h->stream));
+  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n_in * isb, cudaMemcpyHostToDevice, h->stream));
   size_t got = 0;
   rc = sdrg_iqbb_process_dev(h, h->d_in, n_in, h->d_out, total, &got, h->stream);
   if (rc) return rc;
@@ -957,6 +977,80 @@ static int envelope_host(bool usb, int scalar, const void *in, size_t n, void *o
 int sdrg_amdemod_process(int scalar, const void *in, size_t n, void *out) { return envelope_host(false, scalar, in, n, out); }
 int sdrg_usbdemod_process(int scalar, const void *in, size_t n, void *out) { return envelope_host(true, scalar, in, n, out); }
 
+// ---- AutoCast / FMDeemph ----------------------------------------------------------------------------
+int sdrg_autocast_process_dev(int in_type, int out_type, const void *d_in, size_t n, void *d_out, void *stream) {
+  if (out_type != SDRG_T_CS16 || (in_type != SDRG_T_CU8 && in_type != SDRG_T_CS8))
+    return set_error(SDRG_ERR_CONFIG, "AutoCast: Can not cast from type %s (%d) to %s (%d)", type_name(in_type), in_type,
+                     type_name(out_type), out_type);
+  return launch_autocast_cs16(in_type == SDRG_T_CU8 ? 2 : 3, d_in, 2 * n, d_out, (cudaStream_t)stream);
+}
+int sdrg_autocast_process(int in_type, int out_type, const void *in, size_t n, void *out) {
+  if (!n) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(g_device));
+  void *d = nullptr;
+  int rc = sdrg_scratch(2 * n + 4 * n, &d);
+  if (rc) return rc;
+  SDRG_CUDA(cudaMemcpy(d, in, 2 * n, cudaMemcpyHostToDevice));
+  rc = sdrg_autocast_process_dev(in_type, out_type, d, n, (char *)d + ((2 * n + 15) & ~(size_t)15), 0);
+  if (rc) return rc;
+  SDRG_CUDA(cudaMemcpy(out, (char *)d + ((2 * n + 15) & ~(size_t)15), 4 * n, cudaMemcpyDeviceToHost));
+  return SDRG_OK;
+}
+
+struct sdrg_fmdeemph_impl { int device; size_t streams; int alpha; bool enabled; void *d_avg; };
+int sdrg_fmdeemph_create(size_t streams, sdrg_fmdeemph **out) {
+  if (!out || !streams) return set_error(SDRG_ERR_ARG, "FMDeemph: bad argument");
+  sdrg_fmdeemph_impl *h = new sdrg_fmdeemph_impl{g_device, streams, 0, true, nullptr};
+  *out = (sdrg_fmdeemph *)h;
+  return SDRG_OK;
+}
+int sdrg_fmdeemph_destroy(sdrg_fmdeemph *hh) {
+  sdrg_fmdeemph_impl *h = (sdrg_fmdeemph_impl *)hh;
+  if (!h) return SDRG_OK;
+  cudaSetDevice(h->device); cudaDeviceSynchronize();
+  if (h->d_avg) cudaFree(h->d_avg);
+  delete h;
+  return SDRG_OK;
+}
+int sdrg_fmdeemph_configure(sdrg_fmdeemph *hh, const sdrg_config *src, sdrg_config *out) {
+  sdrg_fmdeemph_impl *h = (sdrg_fmdeemph_impl *)hh;
+  if (!h || !src) return set_error(SDRG_ERR_ARG, "null argument");
+  if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
+  if (src->type == SDRG_T_UNDEFINED || src->sample_rate == 0 || src->buffer_size == 0) return SDRG_OK;   // demod.hh:300
+  if (src->type != SDRG_T_S16)
+    return set_error(SDRG_ERR_CONFIG, "Can not configure FMDeemph: Invalid type %s (%d), expected %s (%d)",
+                     type_name(src->type), src->type, type_name(SDRG_T_S16), SDRG_T_S16);
+  h->alpha = (int)round(1.0 / ((1.0 - exp(-1.0 / (src->sample_rate * 75e-6)))));   // demod.hh:309-310
+  SDRG_CUDA(cudaSetDevice(h->device));
+  if (!h->d_avg) SDRG_CUDA(cudaMalloc(&h->d_avg, h->streams * 2));
+  SDRG_CUDA(cudaDeviceSynchronize());
+  SDRG_CUDA(cudaMemset(h->d_avg, 0, h->streams * 2));                              // _avg = 0
+  if (out) { out->type = SDRG_T_S16; out->sample_rate = src->sample_rate; out->buffer_size = src->buffer_size; out->num_buffers = 1; }
+  return SDRG_OK;
+}
+int sdrg_fmdeemph_process_dev(sdrg_fmdeemph *hh, const void *d_in, size_t n, size_t stride, void *d_out, void *stream) {
+  sdrg_fmdeemph_impl *h = (sdrg_fmdeemph_impl *)hh;
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (!h->alpha) return set_error(SDRG_ERR_RUNTIME, "FMDeemph: process() before config()");
+  SDRG_CUDA(cudaSetDevice(h->device));
+  return launch_fmdeemph(d_in, d_out, n, h->streams, stride, h->alpha, h->d_avg, (cudaStream_t)stream);
+}
+int sdrg_fmdeemph_process(sdrg_fmdeemph *hh, const void *in, size_t n, size_t stride, void *out) {
+  sdrg_fmdeemph_impl *h = (sdrg_fmdeemph_impl *)hh;
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (!n) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  const size_t bytes = ((h->streams - 1) * stride + n) * 2;
+  void *d = nullptr;
+  int rc = sdrg_scratch(bytes, &d);
+  if (rc) return rc;
+  SDRG_CUDA(cudaMemcpy(d, in, bytes, cudaMemcpyHostToDevice));
+  rc = sdrg_fmdeemph_process_dev(hh, d, n, stride, d, 0);        // in place is safe: one thread per stream
+  if (rc) return rc;
+  SDRG_CUDA(cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost));
+  return SDRG_OK;
+}
+
 // ---- receive chain -------------------------------------------------------------------------------
 int sdrg_rxchain_create(sdrg_iqbb *bb, int demod, sdrg_rxchain **out) {
   if (!bb || !out) return set_error(SDRG_ERR_ARG, "null argument");
@@ -1018,7 +1112,7 @@ int sdrg_rxchain_process_dev(sdrg_rxchain *h, const void *d_in, size_t buffer_si
   while (done_b < n_buffers) {
     const size_t nb = (n_buffers - done_b) < per_call ? (n_buffers - done_b) : per_call;
     uint64_t got = 0;
-    rc = run_call(bb, (const char *)d_in + done_b * buffer_size * sb, (uint32_t)(nb * buffer_size),
+    rc = run_call(bb, (const char *)d_in + done_b * buffer_size * in_sample_bytes(bb), (uint32_t)(nb * buffer_size),
                   d_bb ? (char *)d_bb + produced * sb : nullptr,
                   (d_audio && h->demod != SDRG_DEMOD_NONE) ? (char *)d_audio + produced * ab : nullptr,
                   h->demod, buffer_size, 1, h->d_last[h->parity], h->d_last[h->parity ^ 1],
@@ -1045,10 +1139,11 @@ int sdrg_rxchain_process(sdrg_rxchain *h, const void *in, size_t buffer_size, si
   const size_t total = (size_t)advance(bb, n_in).n_out;
   if (total > out_cap) return set_error(SDRG_ERR_RUNTIME, "rxchain: output buffers too small (%zu < %zu)", out_cap, total);
   const size_t sb = sample_bytes(bb->d.scalar), ab = audio_bytes(bb->d.scalar, h->demod);
-  if ((rc = grow(&h->d_in, &h->in_cap, n_in * sb))) return rc;
+  const size_t isb = in_sample_bytes(bb);
+  if ((rc = grow(&h->d_in, &h->in_cap, n_in * isb))) return rc;
   if ((rc = grow(&h->d_bb, &h->bb_cap, (total + 1) * sb))) return rc;
   if ((rc = grow(&h->d_audio, &h->audio_cap, (total + 1) * (ab ? ab : 1)))) return rc;
-  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n_in * sb, cudaMemcpyHostToDevice, bb->stream));
+  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n_in * isb, cudaMemcpyHostToDevice, bb->stream));
   size_t got = 0;
   rc = sdrg_rxchain_process_dev(h, h->d_in, buffer_size, n_buffers, h->d_bb, h->d_audio, total, &got, counts, bb->stream);
   if (rc) return rc;

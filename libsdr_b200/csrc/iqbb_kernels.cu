@@ -37,6 +37,18 @@ __device__ __forceinline__ void unpack16(uint32_t v, int &re, int &im) {
   im = ((int)v) >> 16;
 }
 
+// One input sample as packed (re | im << 16) int16 pair.  fmt 0: complex<int16_t> as is; fmt 2/3:
+// AutoCast< complex<int16_t> > fused into the load (src/autocast.hh:187-204): complex uint8 read
+// through an int8_t pointer, (v - 127) << 8 (reference quirk), resp. complex int8, v << 8.
+__device__ __forceinline__ uint32_t load_cs16(const void *base, int64_t idx, uint32_t fmt) {
+  if (fmt == 0) return ((const uint32_t *)base)[idx];
+  const char2 s = ((const char2 *)base)[idx];
+  const int bias = fmt == 2 ? 127 : 0;
+  const uint32_t re = (uint32_t)(uint16_t)(int16_t)(((int)s.x - bias) << 8);
+  const uint32_t im = (uint32_t)(uint16_t)(int16_t)(((int)s.y - bias) << 8);
+  return re | (im << 16);
+}
+
 // window bookkeeping (call-relative sample index i): q(i) = r0 + i - (first && i>0); slot = q/ss.
 // n <= 2^30 and r0 < ss <= 2^30, so q and every window bound fit in 32 bits (the 64-bit division
 // this used to be cost more than the FIR itself).
@@ -61,13 +73,19 @@ __device__ __forceinline__ void prologue(const IqbbAccumArgs &a) {
     nxt[k] = zero;
   }
   if (blockIdx.x == 0) {
-    const Sample *x = (const Sample *)a.x;
-    const Sample *hi = (const Sample *)a.hist_in;
-    Sample *ho = (Sample *)a.hist_out;
     const int64_t H = a.hist_len, n = a.n;
-    for (int64_t k = threadIdx.x; k < H; k += blockDim.x) {
-      const int64_t i = n - H + k;                       // call-relative source index
-      ho[k] = (i >= 0) ? x[i] : hi[H + i];
+    if (sizeof(Sample) == 4 && a.in_fmt != 0) {          // fused AutoCast: the history holds raw 8-bit pairs
+      const char2 *x = (const char2 *)a.x, *hi = (const char2 *)a.hist_in;
+      char2 *ho = (char2 *)a.hist_out;
+      for (int64_t k = threadIdx.x; k < H; k += blockDim.x) { const int64_t i = n - H + k; ho[k] = (i >= 0) ? x[i] : hi[H + i]; }
+    } else {
+      const Sample *x = (const Sample *)a.x;
+      const Sample *hi = (const Sample *)a.hist_in;
+      Sample *ho = (Sample *)a.hist_out;
+      for (int64_t k = threadIdx.x; k < H; k += blockDim.x) {
+        const int64_t i = n - H + k;                     // call-relative source index
+        ho[k] = (i >= 0) ? x[i] : hi[H + i];
+      }
     }
   }
 }
@@ -139,8 +157,8 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs 
       else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
       v = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
     } else {
-      if (i < 0) v = ((const uint32_t *)a.hist_in)[H + i];
-      else if (i < (int64_t)a.n) v = ((const uint32_t *)a.x)[i];
+      if (i < 0) v = load_cs16(a.hist_in, H + i, a.in_fmt);
+      else if (i < (int64_t)a.n) v = load_cs16(a.x, i, a.in_fmt);
     }
     xs[pad32(k)] = v;
   }
@@ -235,9 +253,11 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccu
         const char2 s = xg[k];
         xs[k] = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
       }
-    } else {
+    } else if (a.in_fmt == 0) {
       const uint32_t *xg = (const uint32_t *)a.x + (tile_base - H);
       for (int k = tid; k < n_xs; k += kT) xs[k] = xg[k];
+    } else {
+      for (int k = tid; k < n_xs; k += kT) xs[k] = load_cs16(a.x, tile_base - H + k, a.in_fmt);
     }
   } else {
     for (int k = tid; k < n_xs; k += kT) {
@@ -249,8 +269,8 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccu
         else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
         v = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
       } else {
-        if (i < 0) { if (Hh + i >= 0) v = ((const uint32_t *)a.hist_in)[Hh + i]; }
-        else if (i < (int64_t)a.n) v = ((const uint32_t *)a.x)[i];
+        if (i < 0) { if (Hh + i >= 0) v = load_cs16(a.hist_in, Hh + i, a.in_fmt); }
+        else if (i < (int64_t)a.n) v = load_cs16(a.x, i, a.in_fmt);
       }
       xs[k] = v;
     }

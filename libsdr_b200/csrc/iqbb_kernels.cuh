@@ -30,6 +30,7 @@ struct IqbbAccumArgs {
   uint32_t    nco;        // 0: lut_inc == 0, the mixer is bypassed entirely (freqshift.hh:61)
   uint32_t    neg;        // negative frequency shift: idx = 127 - idx
   uint32_t    zero_next;
+  uint32_t    in_fmt;     // int16 path only: 0 = complex<int16_t> input, 2 = complex uint8, 3 = complex int8 (fused AutoCast)
 };
 
 // One process() call of the folded float kernel (iqbb_fold_kernels.cu)
@@ -98,5 +99,9 @@ int launch_fmdemod(int scalar, const void *in, size_t n, void *out, const void *
                    int in_place, cudaStream_t st);
 int launch_amdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t st);
 int launch_usbdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t st);
+// AutoCast<complex<int16_t>> from complex uint8 (fmt 2) / int8 (fmt 3): n_bytes in, n_bytes int16 out
+int launch_autocast_cs16(int fmt, const void *in, size_t n_bytes, void *out, cudaStream_t st);
+// FMDeemph<int16_t>: `streams` independent sequences of n samples (stride elements apart), one thread each
+int launch_fmdeemph(const void *in, void *out, size_t n, size_t streams, size_t stride, int alpha, void *avg, cudaStream_t st);
 
 }  // namespace sdrg

@@ -75,6 +75,12 @@ class IQBaseBand:
     def setSubsample(self, ss): _lib.call("sdrg_iqbb_set_subsample", self._h, int(ss))
     def setOutputSampleRate(self, fs): _lib.call("sdrg_iqbb_set_output_sample_rate", self._h, float(fs))
 
+    def setInputType(self, type_id):
+        """int16 only: consume complex uint8 / int8 input with AutoCast<complex<int16>> fused into the load."""
+        _lib.call("sdrg_iqbb_set_input_type", self._h, int(type_id))
+        self.in_dtype = {_lib.T_CU8: np.uint8, _lib.T_CS8: np.int8}.get(int(type_id), self.dtype)
+        self._in_type = int(type_id)
+
     def setFloatPath(self, mode):
         """f32 only: 0 auto, 1 direct kernel, 2 folded kernel (before config())."""
         _lib.call("sdrg_iqbb_set_float_path", self._h, int(mode))
@@ -98,7 +104,7 @@ class IQBaseBand:
         return out
 
     def _ctype(self):
-        return _CTYPE[self.scalar]
+        return getattr(self, "_in_type", _CTYPE[self.scalar])
 
     def info(self):
         inf = _lib.IqbbInfo()
@@ -124,12 +130,13 @@ class IQBaseBand:
             import torch
             n_in = x.shape[0]
             n_out = self.outputs_for(n_in)
-            out = torch.empty((max(n_out, 1), 2), dtype=x.dtype, device=x.device)
+            odt = {np.int8: torch.int8, np.int16: torch.int16, np.float32: torch.float32}[self.dtype]
+            out = torch.empty((max(n_out, 1), 2), dtype=odt, device=x.device)
             got = C.c_size_t(0)
             _lib.call("sdrg_iqbb_process_dev", self._h, C.c_void_p(x.data_ptr()), n_in,
                       C.c_void_p(out.data_ptr()), n_out, C.byref(got), _stream_ptr())
             return out[:got.value]
-        x = np.ascontiguousarray(x, dtype=self.dtype).reshape(-1, 2)
+        x = np.ascontiguousarray(x, dtype=getattr(self, "in_dtype", self.dtype)).reshape(-1, 2)
         n_out = self.outputs_for(x.shape[0])
         out = np.zeros((n_out, 2), dtype=self.dtype)
         got = C.c_size_t(0)
@@ -251,14 +258,15 @@ class RxChain:
             import torch
             adt = {np.int16: torch.int16, np.int8: torch.int8, np.float32: torch.float32}[self.audio_dtype()]
             if bb_out is None:
-                bb_out = torch.empty((max(n_out, 1), 2), dtype=x.dtype, device=x.device)
+                bdt = {np.int16: torch.int16, np.int8: torch.int8, np.float32: torch.float32}[self.bb.dtype]
+                bb_out = torch.empty((max(n_out, 1), 2), dtype=bdt, device=x.device)
             if audio_out is None:
                 audio_out = torch.zeros(max(n_out, 1), dtype=adt, device=x.device)
             _lib.call("sdrg_rxchain_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb,
                       C.c_void_p(bb_out.data_ptr()), C.c_void_p(audio_out.data_ptr()), n_out,
                       C.byref(got), counts, _stream_ptr())
             return bb_out[:got.value], audio_out[:got.value], np.array(counts[:], dtype=np.int64)
-        x = np.ascontiguousarray(x, dtype=self.bb.dtype).reshape(-1, 2)
+        x = np.ascontiguousarray(x, dtype=getattr(self.bb, "in_dtype", self.bb.dtype)).reshape(-1, 2)
         if bb_out is None:
             bb_out = np.zeros((n_out, 2), dtype=self.bb.dtype)
         if audio_out is None:
@@ -437,3 +445,56 @@ class ChannelBank:
         _lib.call("sdrg_bank_process", self._h, _np_ptr(x), buffer_size, nb, ptr("bb"), ptr("fm"), ptr("am"), ptr("usb"),
                   stride, C.byref(got))
         return {k: res[k][:, :got.value] for k in want}
+
+
+def autocast_cs16(x):
+    """AutoCast< complex<int16> > of complex uint8 / int8 samples (n, 2) (src/autocast.hh:187-204)."""
+    if _is_torch(x):
+        import torch
+        t = _lib.T_CU8 if x.dtype == torch.uint8 else _lib.T_CS8
+        out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+        _lib.call("sdrg_autocast_process_dev", t, _lib.T_CS16, C.c_void_p(x.data_ptr()), x.shape[0], C.c_void_p(out.data_ptr()), _stream_ptr())
+        return out
+    x = np.ascontiguousarray(x)
+    t = _lib.T_CU8 if x.dtype == np.uint8 else _lib.T_CS8
+    out = np.zeros(x.shape, dtype=np.int16)
+    _lib.call("sdrg_autocast_process", t, _lib.T_CS16, _np_ptr(x), x.shape[0], _np_ptr(out))
+    return out
+
+
+class FMDeemph:
+    """FMDeemph<int16_t> (src/demod.hh:271-362) for `streams` independent audio streams (rows)."""
+
+    def __init__(self, streams=1):
+        self.streams = int(streams)
+        self._h = C.c_void_p()
+        _lib.call("sdrg_fmdeemph_create", self.streams, C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_fmdeemph_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def config(self, src_cfg=None, *, sample_rate=0.0, buffer_size=0, type=_lib.T_S16):
+        if src_cfg is None:
+            src_cfg = Config(type, sample_rate, buffer_size, 1)
+        out = Config()
+        _lib.call("sdrg_fmdeemph_configure", self._h, C.byref(src_cfg), C.byref(out))
+        return out
+
+    def process(self, x):
+        """x: (streams, n) int16 (or (n,) for one stream)."""
+        if _is_torch(x):
+            import torch
+            x2 = x.view(self.streams, -1)
+            out = torch.empty_like(x2)
+            _lib.call("sdrg_fmdeemph_process_dev", self._h, C.c_void_p(x2.data_ptr()), x2.shape[1], x2.stride(0),
+                      C.c_void_p(out.data_ptr()), _stream_ptr())
+            return out.view(x.shape)
+        x2 = np.ascontiguousarray(x, dtype=np.int16).reshape(self.streams, -1)
+        out = np.zeros_like(x2)
+        _lib.call("sdrg_fmdeemph_process", self._h, _np_ptr(x2), x2.shape[1], x2.shape[1], _np_ptr(out))
+        return out.reshape(np.shape(x))
