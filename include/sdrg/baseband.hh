@@ -34,6 +34,14 @@ public:
   size_t subSample() const { return info().sub_sample; }
   void setSubsample(size_t ss) { gpu::check(sdrg_iqbb_set_subsample(_h, ss)); republish(); }
   void setOutputSampleRate(double Fs) { gpu::check(sdrg_iqbb_set_output_sample_rate(_h, Fs)); republish(); }
+  /** int16_t only: consume complex uint8 / int8 buffers directly, AutoCast fused into the load
+   * (call before the node is configured; handleBuffer() then reinterprets the raw bytes). */
+  void setInputType(Config::Type type) { gpu::check(sdrg_iqbb_set_input_type(_h, (int)type)); _raw8 = (type == Config::Type_cu8 || type == Config::Type_cs8); }
+  virtual void handleBuffer(const RawBuffer &buffer, bool allow_overwrite) {
+    if (!_raw8) { Sink<CScalar>::handleBuffer(buffer, allow_overwrite); return; }
+    if (!_buffer.isUnused()) return;
+    run_raw(buffer, buffer.bytesLen() / 2);
+  }
 
   virtual bool acceptsDeviceBuffers() const { return true; }
 
@@ -44,7 +52,7 @@ public:
     if (SDRG_T_UNDEFINED == out.type) return;         // incomplete config: ignored (baseband.hh:118)
     _src = src_cfg; _out = out;
     _buffer.unref();
-    _buffer = Buffer<CScalar>(out.buffer_size);
+    _buffer = Buffer<CScalar>(out.buffer_size, 0, true);
     LogMessage msg(LOG_DEBUG);
     msg << "Configured IQBaseBand node (B200):" << std::endl
         << " type " << src_cfg.type() << std::endl << " sample-rate " << src_cfg.sampleRate() << "Hz" << std::endl
@@ -65,6 +73,24 @@ protected:
   void republish() {    // the rate setters reconfigure and publish a new output config (baseband.hh:156-194)
     if (!_src.hasType() || !_src.hasSampleRate() || !_src.hasBufferSize()) return;
     config(_src);
+  }
+  void run_raw(const RawBuffer &in, size_t n_in) {       // fused AutoCast: always out of place (2-byte samples in)
+    void *st = gpu::stream();
+    const void *d_in = gpu::deviceInput(in, st);
+    size_t n_out = 0;
+    gpu::check(sdrg_iqbb_outputs_for(_h, n_in, &n_out));
+    void *d_out = gpu::deviceOutput(_buffer);
+    if (d_out) {
+      gpu::check(sdrg_iqbb_process_dev(_h, d_in, n_in, d_out, _buffer.size(), &n_out, st));
+      if (n_out) gpu::publish(_buffer, n_out * sizeof(CScalar), st);
+    } else {                                  // no CUDA-backed storage (should not happen on a GPU box)
+      void *d_tmp = 0;
+      gpu::check(sdrg_scratch((n_out + 1) * sizeof(CScalar), &d_tmp));
+      gpu::check(sdrg_iqbb_process_dev(_h, d_in, n_in, d_tmp, _buffer.size(), &n_out, st));
+      gpu::check(sdrg_memcpy_d2h_async(_buffer.data(), d_tmp, n_out * sizeof(CScalar), st));
+      gpu::check(sdrg_stream_synchronize(st));
+    }
+    this->send(_buffer.head(n_out), true);
   }
   void run(const Buffer<CScalar> &in, const Buffer<CScalar> &out) {
     void *st = gpu::stream();
@@ -88,6 +114,7 @@ protected:
   }
 
   sdrg_iqbb *_h;
+  bool _raw8 = false;
   Config _src;
   sdrg_config _out;
   Buffer<CScalar> _buffer;

@@ -45,9 +45,9 @@ struct Storage {
   BufferOwner *owner;
   bool managed;            // allocated by sdrg_buffer_alloc (pinned + device mirror)
   static constexpr size_t kManagedThreshold = 4096;   // smaller buffers never travel to the GPU in bulk
-  static char *allocate(size_t bytes, bool &managed) {
+  static char *allocate(size_t bytes, bool &managed, bool force_device) {
     managed = false;
-    if (bytes >= kManagedThreshold) {
+    if (bytes >= kManagedThreshold || (force_device && bytes > 0)) {
       void *p = 0;
       if (SDRG_OK == sdrg_buffer_alloc(bytes, &p) && p) { managed = true; return (char *)p; }
     }
@@ -66,11 +66,12 @@ public:
   /** Wraps memory the buffer does not own (never counted, never freed). */
   RawBuffer(char *data, size_t offset, size_t len)
     : _ptr(data), _storage_size(offset + len), _b_offset(offset), _b_length(len), _st(0) {}
-  /** Allocates N bytes; the new buffer holds the one and only reference. */
-  RawBuffer(size_t N, BufferOwner *owner = 0)
+  /** Allocates N bytes; the new buffer holds the one and only reference.  `device_backed` asks for
+   * pinned + device-mirrored storage whatever the size (GPU nodes do so for their output buffers). */
+  RawBuffer(size_t N, BufferOwner *owner = 0, bool device_backed = false)
     : _ptr(0), _storage_size(0), _b_offset(0), _b_length(0), _st(0) {
     bool managed = false;
-    char *p = detail::Storage::allocate(N, managed);
+    char *p = detail::Storage::allocate(N, managed, device_backed);
     if (!p) return;
     _st = new detail::Storage();
     _st->refs.store(1); _st->owner = owner; _st->managed = managed;
@@ -125,7 +126,7 @@ class Buffer : public RawBuffer {
 public:
   Buffer() : RawBuffer(), _size(0) {}
   Buffer(T *data, size_t size) : RawBuffer((char *)data, 0, sizeof(T) * size), _size(size) {}
-  Buffer(size_t N, BufferOwner *owner = 0) : RawBuffer(N * sizeof(T), owner), _size(N) {}
+  Buffer(size_t N, BufferOwner *owner = 0, bool device_backed = false) : RawBuffer(N * sizeof(T), owner, device_backed), _size(N) {}
   Buffer(const Buffer<T> &o) : RawBuffer(o), _size(o._size) {}
   /** Reinterprets the bytes of any buffer as elements of T. */
   explicit Buffer(const RawBuffer &o) : RawBuffer(o), _size(o.bytesLen() / sizeof(T)) {}

@@ -55,7 +55,7 @@ public:
     gpu::check(sdrg_amdemod_configure(Traits<Scalar>::scalarId, &in, &out));
     if (SDRG_T_UNDEFINED == out.type) return;
     this->_buffer.unref();
-    this->_buffer = Buffer<Scalar>(src_cfg.bufferSize());
+    this->_buffer = Buffer<Scalar>(src_cfg.bufferSize(), 0, true);
     this->setConfig(Config::from(out));
   }
   virtual void process(const Buffer< std::complex<Scalar> > &buffer, bool allow_overwrite) {
@@ -75,7 +75,7 @@ public:
     gpu::check(sdrg_usbdemod_configure(Traits<Scalar>::scalarId, &in, &out));
     if (SDRG_T_UNDEFINED == out.type) return;
     this->_buffer.unref();
-    this->_buffer = Buffer<Scalar>(src_cfg.bufferSize());
+    this->_buffer = Buffer<Scalar>(src_cfg.bufferSize(), 0, true);
     this->setConfig(Config::from(out));
   }
   virtual void process(const Buffer< std::complex<Scalar> > &buffer, bool allow_overwrite) {
@@ -102,7 +102,7 @@ public:
       throw err;
     }
     this->_buffer.unref();
-    this->_buffer = Buffer<oScalar>(src_cfg.bufferSize());
+    this->_buffer = Buffer<oScalar>(src_cfg.bufferSize(), 0, true);
     _can_overwrite = (sizeof(std::complex<iScalar>) >= sizeof(oScalar));
     this->setConfig(Config::from(out));
   }
@@ -116,6 +116,48 @@ public:
 protected:
   sdrg_fmdemod *_h;
   bool _can_overwrite;
+};
+
+
+/** FM de-emphasis (src/demod.hh:271-362): integer 1-pole IIR with rounding, 75 us time constant. */
+template <class Scalar>
+class FMDeemph : public Sink<Scalar>, public Source {
+public:
+  FMDeemph(bool enabled = true) : Sink<Scalar>(), Source(), _enabled(enabled), _h(0) {
+    static_assert(sizeof(Scalar) == 2, "the device FMDeemph is implemented for int16_t");
+    gpu::check(sdrg_fmdeemph_create(1, &_h));
+  }
+  virtual ~FMDeemph() { sdrg_fmdeemph_destroy(_h); _buffer.unref(); }
+  inline bool isEnabled() const { return _enabled; }
+  inline void enable(bool enabled) { _enabled = enabled; }
+  virtual bool acceptsDeviceBuffers() const { return true; }
+  virtual void config(const Config &src_cfg) {
+    const sdrg_config in = src_cfg.c(); sdrg_config out;
+    gpu::check(sdrg_fmdeemph_configure(_h, &in, &out));
+    if (SDRG_T_UNDEFINED == out.type) return;
+    _buffer.unref();
+    _buffer = Buffer<Scalar>(src_cfg.bufferSize(), 0, true);
+    this->setConfig(Config::from(out));
+  }
+  virtual void process(const Buffer<Scalar> &buffer, bool allow_overwrite) {
+    if (!_enabled) { this->send(buffer, allow_overwrite); return; }
+    const Buffer<Scalar> out = allow_overwrite ? buffer : _buffer;
+    const size_t n = buffer.size();
+    void *st = gpu::stream();
+    const void *d_in = gpu::deviceInput(buffer, st);
+    void *d_out = allow_overwrite ? const_cast<void *>(d_in) : gpu::deviceOutput(out);
+    const bool mirrored = 0 != gpu::deviceOutput(out);
+    void *d_tmp = 0;
+    if (!d_out) { gpu::check(sdrg_scratch(n * sizeof(Scalar), &d_tmp)); d_out = d_tmp; }
+    gpu::check(sdrg_fmdeemph_process_dev(_h, d_in, n, n, d_out, st));    // one thread per stream: in place is safe
+    if (mirrored) gpu::publish(out, n * sizeof(Scalar), st);
+    else { gpu::check(sdrg_memcpy_d2h_async(out.data(), d_out, n * sizeof(Scalar), st)); gpu::check(sdrg_stream_synchronize(st)); }
+    this->send(out.head(n), allow_overwrite);
+  }
+protected:
+  bool _enabled;
+  sdrg_fmdeemph *_h;
+  Buffer<Scalar> _buffer;
 };
 
 }  // namespace sdr

@@ -73,13 +73,13 @@ protected:
     // room for everything one input buffer can release: (pending + bufferSize) rounded down to blocks
     _cap = ((cfg.bufferSize() + _block - 1) / _block + 1) * _block;
     _out.unref();
-    _out = Buffer<C>(_cap * (_filters.empty() ? 1 : _filters.size()));
+    _out = Buffer<C>(_cap * (_filters.empty() ? 1 : _filters.size()), 0, true);
     for (typename std::list<FilterSource<Scalar> *>::iterator it = _filters.begin(); it != _filters.end(); ++it)
       (*it)->setConfig(Config(Config::Type_cf32, cfg.sampleRate(), _block, cfg.numBuffers()));
   }
   void run(const Buffer<C> &in) {
     if (_filters.empty()) return;
-    if (_out.size() < _cap * _filters.size()) { _out.unref(); _out = Buffer<C>(_cap * _filters.size()); }
+    if (_out.size() < _cap * _filters.size()) { _out.unref(); _out = Buffer<C>(_cap * _filters.size(), 0, true); }
     if (!_out.isUnused()) return;                 // downstream still holds the previous output: drop (like the reference's nodes)
     void *st = gpu::stream();
     const void *d_in = gpu::deviceInput(in, st);

@@ -10,6 +10,7 @@
 #include "node.hh"
 #include "baseband.hh"
 #include "demod.hh"
+#include "autocast.hh"
 #include "fftplan.hh"
 #include "filternode.hh"
 #endif

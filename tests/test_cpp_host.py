@@ -11,11 +11,12 @@ BUILD = os.path.join(ROOT, "build", "tests")
 LIBDIR = os.path.join(ROOT, "libsdr_b200")
 
 
-def compile_cpp(name, extra=()):
+def compile_cpp(name, extra=(), compat=False):
     os.makedirs(BUILD, exist_ok=True)
     out = os.path.join(BUILD, name)
     src = os.path.join(ROOT, "tests", "cpp", name + ".cc")
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), src] + list(extra) + [
+    inc = ["-I" + os.path.join(ROOT, "include")] + (["-I" + os.path.join(ROOT, "include", "sdrg", "compat")] if compat else [])
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall"] + inc + [src] + list(extra) + [
         "-o", out, "-L" + LIBDIR, "-l:libsdrg.so", "-Wl,-rpath," + LIBDIR, "-lpthread", "-lm"]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     return out
@@ -57,3 +58,14 @@ def test_filternode_and_fftplan_classes():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "filter_test: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_full_sdr_fm_chain_with_reference_header_names():
+    os.makedirs(BUILD, exist_ok=True)
+    obj = os.path.join(BUILD, "sdr_oracle.o")
+    subprocess.run(["gcc", "-O2", "-fwrapv", "-c", os.path.join(ROOT, "oracle", "sdr_oracle.c"), "-o", obj], check=True)
+    exe = compile_cpp("sdr_fm_test", extra=[obj], compat=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sdr_fm_test: ok" in r.stdout
