@@ -117,6 +117,98 @@ __device__ float2 *fft_smem(float2 *a, float2 *b, float2 *c, const int n, const 
   return const_cast<float2 *>(src);
 }
 
+// ---- in-place variant -------------------------------------------------------------------------------
+// The same stages on ONE shared buffer: every thread first pulls all the inputs of its butterflies
+// into registers, the CTA synchronises, then the outputs are written (two barriers per stage instead
+// of one, half the shared memory -> two resident CTAs of 1024 threads per SM for the 8192-point
+// transform).  B = butterflies per thread (n/R/blockDim), at most 8/R * 8... kept <= 8 elements/thread
+// for n <= 8 * blockDim.
+template <int R, bool INV, int B>
+__device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const int n, const int Ns,
+                                              const float2 *__restrict__ tw, const float2 *__restrict__ mul) {
+  const int nb = n / R;
+  const int tstep = n / (Ns * R);
+  float2 v[B][R];
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    const int j = threadIdx.x + b * blockDim.x;
+    if (j < nb) {
+      const int k = j & (Ns - 1);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        v[b][r] = buf[pidx(j + r * nb)];
+        if (mul) v[b][r] = cmulf(v[b][r], __ldg(mul + j + r * nb));
+      }
+      if (k > 0) {
+        float2 w1 = __ldg(tw + k * tstep);
+        if (INV) w1.y = -w1.y;
+        v[b][1] = cmulf(v[b][1], w1);
+        if (R > 2) {
+          const float2 w2 = cmulf(w1, w1), w3 = cmulf(w2, w1);
+          v[b][2] = cmulf(v[b][2], w2); v[b][3] = cmulf(v[b][3], w3);
+          if (R > 4) {
+            const float2 w4 = cmulf(w2, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
+            v[b][4] = cmulf(v[b][4], w4); v[b][5] = cmulf(v[b][5], w5); v[b][6] = cmulf(v[b][6], w6); v[b][7] = cmulf(v[b][7], w7);
+          }
+        }
+      }
+      if (R == 2) dft2<INV>(v[b][0], v[b][1]);
+      else if (R == 4) dft4<INV>(v[b]);
+      else dft8<INV>(v[b]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    const int j = threadIdx.x + b * blockDim.x;
+    if (j < nb) {
+      const int k = j & (Ns - 1);
+      const int base = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) buf[pidx(base + r * Ns)] = v[b][r];
+    }
+  }
+  __syncthreads();
+}
+
+// n = EPT * blockDim.x points: EPT/8 radix-8, EPT/4 radix-4 or EPT/2 radix-2 butterflies per thread
+template <bool INV, int EPT>
+__device__ void fft_smem_inplace(float2 *buf, const int n, const int log2n, const float2 *tw, const float2 *mul) {
+  int Ns = 1, left = log2n;
+  bool first = true;
+  while (left > 0) {
+    const float2 *m = first ? mul : nullptr;
+    if (left >= 3 && left != 4) { stage_inplace<8, INV, EPT / 8>(buf, n, Ns, tw, m); Ns *= 8; left -= 3; }
+    else if (left >= 2) { stage_inplace<4, INV, EPT / 4>(buf, n, Ns, tw, m); Ns *= 4; left -= 2; }
+    else { stage_inplace<2, INV, EPT / 2>(buf, n, Ns, tw, m); Ns *= 2; left -= 1; }
+    first = false;
+  }
+}
+
+// Single-filter overlap-save with one shared buffer: 16 elements per thread, 512 threads and 72 KB
+// at block 4096 -> two (register-limited) resident CTAs per SM whose barrier phases overlap.
+__global__ void __launch_bounds__(512, 2) filter_ola1_kernel(const FilterArgs a) {
+  extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+  const int N = a.block, n = 2 * N;
+  float2 *s0 = (float2 *)fft_smem_raw;
+  const int b = blockIdx.x;
+  const float2 *x = (const float2 *)a.x;
+  const float2 *prev = b == 0 ? (const float2 *)a.hist_in : x + (size_t)(b - 1) * N;
+  const float2 *cur = x + (size_t)b * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { s0[pidx(i)] = prev[i]; s0[pidx(N + i)] = cur[i]; }
+  if (b == (int)gridDim.x - 1) {
+    float2 *ho = (float2 *)a.hist_out;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ho[i] = cur[i];
+  }
+  __syncthreads();
+  const float2 *tw = (const float2 *)a.tw;
+  fft_smem_inplace<false, 16>(s0, n, a.log2n, tw, nullptr);
+  fft_smem_inplace<true, 16>(s0, n, a.log2n, tw, (const float2 *)a.kern);
+  const float sc = 1.0f / (float)n;
+  float2 *o = (float2 *)a.out + (size_t)b * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { const float2 v = s0[pidx(N + i)]; o[i] = make_float2(v.x * sc, v.y * sc); }
+}
+
 // ---- batched plain FFT (FFTPlan<float>::operator()) ---------------------------------------------
 __global__ void __launch_bounds__(1024) fft_batch_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const int n,
                                                           const int log2n, const int inverse, const float2 *__restrict__ tw) {
@@ -187,6 +279,17 @@ int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
     attr = smem;
   }
   int threads = n / 8; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
+  if (a.n_filters == 1 && n >= 512) {          // one filter: in-place stages on a single buffer (n == 16 * threads)
+    const size_t smem1 = (size_t)padded_len(n) * sizeof(float2);
+    static size_t attr1 = 0;
+    if (smem1 > 48 * 1024 && smem1 > attr1) {
+      SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      attr1 = smem1;
+    }
+    filter_ola1_kernel<<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
+    SDRG_CHECK_LAUNCH("filter_ola1_kernel");
+    return SDRG_OK;
+  }
   filter_ola_kernel<<<(unsigned)n_blocks, threads, smem, st>>>(a);
   SDRG_CHECK_LAUNCH("filter_ola_kernel");
   return SDRG_OK;
