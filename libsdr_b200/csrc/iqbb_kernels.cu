@@ -230,111 +230,136 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs 
 // operand plus one unpack per sample -- no loads, no guards, no address arithmetic.
 struct IqbbTaps { int4 t[32]; };
 
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent CTAs (one per resident slot) walk the tiles grid-stride; the next tile is fetched into
+// the other shared buffer with cp.async (LDGSTS: no registers, no scoreboard stall) while the current
+// one is being filtered, so the global-load latency that used to head every tile is hidden.
 template <int LP, bool IS_S8>
 __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccumArgs a, const __grid_constant__ IqbbTaps taps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int H = LP - 1;
   constexpr int NV = (LP + 7 + 3) / 4;                 // 128-bit loads per thread
   constexpr int n_xs = kTile + 4 * NV + 8;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int xs_pitch = (n_xs + 3) & ~3;
+  const int tid = threadIdx.x;
   int2 *lut = (int2 *)smem_raw;                                   // 128
   int2 *zs = lut + 128;                                          // kR * kZRow
-  uint32_t *xs = (uint32_t *)(zs + kR * kZRow);                  // n_xs, 16-byte aligned
+  uint32_t *xs_all = (uint32_t *)(zs + kR * kZRow);              // 2 x xs_pitch, 16-byte aligned
 
   if (IS_S8) prologue<char2, int2>(a); else prologue<short2, int2>(a);
-
-  const int64_t tile_base = (int64_t)blockIdx.x * kTile;
   if (tid < 128) lut[tid] = ((const int2 *)a.lut)[tid];
   const int Hh = (int)a.hist_len;                                // history kept by the handle (= stripped taps - 1 <= H)
-  if (tile_base >= H && tile_base - H + n_xs <= (int64_t)a.n) {  // interior tile: no bounds, no history
-    if (IS_S8) {
-      const char2 *xg = (const char2 *)a.x + (tile_base - H);
-      for (int k = tid; k < n_xs; k += kT) {
-        const char2 s = xg[k];
-        xs[k] = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
-      }
-    } else if (a.in_fmt == 0) {
-      const uint32_t *xg = (const uint32_t *)a.x + (tile_base - H);
-      for (int k = tid; k < n_xs; k += kT) xs[k] = xg[k];
-    } else {
-      for (int k = tid; k < n_xs; k += kT) xs[k] = load_cs16(a.x, tile_base - H + k, a.in_fmt);
-    }
-  } else {
-    for (int k = tid; k < n_xs; k += kT) {
-      const int64_t i = tile_base - H + k;
-      uint32_t v = 0;
-      if (IS_S8) {
-        char2 s = make_char2(0, 0);
-        if (i < 0) { if (Hh + i >= 0) s = ((const char2 *)a.hist_in)[Hh + i]; }
-        else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
-        v = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
-      } else {
-        if (i < 0) { if (Hh + i >= 0) v = load_cs16(a.hist_in, Hh + i, a.in_fmt); }
-        else if (i < (int64_t)a.n) v = load_cs16(a.x, i, a.in_fmt);
-      }
-      xs[k] = v;
-    }
-  }
-  __syncthreads();
+  const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
 
-  uint32_t w[4 * NV];
+  // stage tile t into xs: asynchronously when it is an interior int16 tile, synchronously otherwise
+  auto stage = [&](uint32_t t, uint32_t *xs) {
+    const int64_t tile_base = (int64_t)t * kTile;
+    const bool interior = tile_base >= H && tile_base - H + n_xs <= (int64_t)a.n;
+    if (interior && !IS_S8 && a.in_fmt == 0) {
+      const uint32_t *xg = (const uint32_t *)a.x + (tile_base - H);
+      for (int k = tid; k < n_xs; k += kT) cp_async4(xs + k, xg + k);
+    } else {
+      for (int k = tid; k < n_xs; k += kT) {
+        const int64_t i = tile_base - H + k;
+        uint32_t v = 0;
+        if (IS_S8) {
+          char2 s = make_char2(0, 0);
+          if (i < 0) { if (Hh + i >= 0) s = ((const char2 *)a.hist_in)[Hh + i]; }
+          else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
+          v = ((uint32_t)(uint16_t)(int16_t)s.x) | (((uint32_t)(uint16_t)(int16_t)s.y) << 16);
+        } else {
+          if (i < 0) { if (Hh + i >= 0) v = load_cs16(a.hist_in, Hh + i, a.in_fmt); }
+          else if (i < (int64_t)a.n) v = load_cs16(a.x, i, a.in_fmt);
+        }
+        xs[k] = v;
+      }
+    }
+    cp_async_commit();
+  };
+
+  uint32_t t = blockIdx.x;
+  if (t < n_tiles) stage(t, xs_all);
+  for (int buf = 0; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    uint32_t *xs = xs_all + buf * xs_pitch;
+    if (t + gridDim.x < n_tiles) { stage(t + gridDim.x, xs_all + (buf ^ 1) * xs_pitch); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int64_t tile_base = (int64_t)t * kTile;
+
+    uint32_t w[4 * NV];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const uint4 q = ((const uint4 *)xs)[tid * 2 + v];
-    w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
-  }
-  uint32_t A1[kR], A2[kR], A3[kR];
-  int wr[kR], wi[kR], ws[kR];
+    for (int v = 0; v < NV; ++v) {
+      const uint4 q = ((const uint4 *)xs)[tid * 2 + v];
+      w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    }
+    uint32_t A1[kR], A2[kR], A3[kR];
+    int wr[kR], wi[kR], ws[kR];
 #pragma unroll
-  for (int c = 0; c < kR; ++c) {
-    A1[c] = A2[c] = A3[c] = 0u;
-    unpack16(w[c], wr[c], wi[c]);
-    ws[c] = wr[c] + wi[c];
-  }
+    for (int c = 0; c < kR; ++c) {
+      A1[c] = A2[c] = A3[c] = 0u;
+      unpack16(w[c], wr[c], wi[c]);
+      ws[c] = wr[c] + wi[c];
+    }
 #pragma unroll
-  for (int t = 0; t < LP; ++t) {
-    const int4 c = taps.t[t];
+    for (int tt = 0; tt < LP; ++tt) {
+      const int4 c = taps.t[tt];
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const int s = (r + tt) & (kR - 1);
+        A1[r] += (uint32_t)c.x * (uint32_t)ws[s];
+        A2[r] += (uint32_t)c.y * (uint32_t)wr[s];
+        A3[r] += (uint32_t)c.z * (uint32_t)wi[s];
+      }
+      if (tt + 1 < LP) {
+        unpack16(w[tt + kR], wr[tt & (kR - 1)], wi[tt & (kR - 1)]);
+        ws[tt & (kR - 1)] = wr[tt & (kR - 1)] + wi[tt & (kR - 1)];
+      }
+    }
+
+    const int ob = tid * kR;
+    const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
+    const uint32_t negx = a.neg ? 127u : 0u;                     // 127 - idx == idx ^ 127 on 0..127
+    uint32_t ph = (a.phase0 + i0 * a.inc) & 0x7fffu;
 #pragma unroll
     for (int r = 0; r < kR; ++r) {
-      const int s = (r + t) & (kR - 1);
-      A1[r] += (uint32_t)c.x * (uint32_t)ws[s];
-      A2[r] += (uint32_t)c.y * (uint32_t)wr[s];
-      A3[r] += (uint32_t)c.z * (uint32_t)wi[s];
+      int yr = ((int)(A1[r] - A3[r])) >> 14;
+      int yi = ((int)(A1[r] + A2[r])) >> 14;
+      if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }
+      if (a.nco) {
+        const int2 l = lut[(ph >> 8) ^ negx];
+        ph = (ph + a.inc) & 0x7fffu;
+        const uint32_t pr = (uint32_t)l.x * (uint32_t)yr - (uint32_t)l.y * (uint32_t)yi;
+        const uint32_t pi = (uint32_t)l.x * (uint32_t)yi + (uint32_t)l.y * (uint32_t)yr;
+        if (IS_S8) { yr = (int)(short)(((int)(short)pr) >> 8); yi = (int)(short)(((int)(short)pi) >> 8); }
+        else { yr = ((int)pr) >> 16; yi = ((int)pi) >> 16; }
+      }
+      zs[r * kZRow + tid] = make_int2(yr, yi);
     }
-    if (t + 1 < LP) {
-      unpack16(w[t + kR], wr[t & (kR - 1)], wi[t & (kR - 1)]);
-      ws[t & (kR - 1)] = wr[t & (kR - 1)] + wi[t & (kR - 1)];
-    }
+    __syncthreads();
+    window_sums_int(a, zs, tile_base, tid);
   }
-
-  const int ob = tid * kR;
-  const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
-#pragma unroll
-  for (int r = 0; r < kR; ++r) {
-    int yr = ((int)(A1[r] - A3[r])) >> 14;
-    int yi = ((int)(A1[r] + A2[r])) >> 14;
-    if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }
-    if (a.nco) {
-      const uint32_t ph = (a.phase0 + (i0 + r) * a.inc) & 0x7fffu;
-      uint32_t idx = ph >> 8;
-      if (a.neg) idx = 127u - idx;
-      const int2 l = lut[idx];
-      const uint32_t pr = (uint32_t)l.x * (uint32_t)yr - (uint32_t)l.y * (uint32_t)yi;
-      const uint32_t pi = (uint32_t)l.x * (uint32_t)yi + (uint32_t)l.y * (uint32_t)yr;
-      if (IS_S8) { yr = (int)(short)(((int)(short)pr) >> 8); yi = (int)(short)(((int)(short)pi) >> 8); }
-      else { yr = ((int)pr) >> 16; yi = ((int)pi) >> 16; }
-    }
-    zs[r * kZRow + tid] = make_int2(yr, yi);
-  }
-  __syncthreads();
-
-  window_sums_int(a, zs, tile_base, tid);
 }
 
 template <int LP, bool IS_S8>
-int launch_fixed(const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned grid, cudaStream_t st) {
+int launch_fixed(const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned n_tiles, cudaStream_t st) {
   constexpr int NV = (LP + 7 + 3) / 4;
-  const size_t smem = sizeof(int2) * 128 + sizeof(int2) * kR * kZRow + sizeof(uint32_t) * (kTile + 4 * NV + 8);
+  constexpr int xs_pitch = (kTile + 4 * NV + 8 + 3) & ~3;
+  const size_t smem = sizeof(int2) * 128 + sizeof(int2) * kR * kZRow + sizeof(uint32_t) * 2 * xs_pitch;
+  static int resident = 0;               // per instantiation: CTAs that fit the device at once
+  if (!resident) {
+    int dev = 0, sms = 0, per_sm = 0;
+    SDRG_CUDA(cudaGetDevice(&dev));
+    SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_accum_int_fixed_kernel<LP, IS_S8>, kT, smem));
+    resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const unsigned grid = n_tiles < (unsigned)resident ? n_tiles : (unsigned)resident;
   iqbb_accum_int_fixed_kernel<LP, IS_S8><<<grid, kT, smem, st>>>(a, taps);
   SDRG_CHECK_LAUNCH("iqbb_accum_int_fixed_kernel");
   return SDRG_OK;
