@@ -224,10 +224,12 @@ def secondary_workloads(world, rank, dev, dist, args):
             return r
 
         ms = maxms(_time_steps(step, 3, 2, barrier))
+        imad_peak = 148 * 64 * 1.965e9           # FMA-heavy pipe: 64 IMAD lanes / clk / SM
         out["c5_bank"] = {"workload": "2048-channel IQBaseBand<int16> bank (15 taps, 100 MS/s -> 48 kHz) + FM + AM, channels "
                                       "sharded over %d GPU(s), NCCL all_gather of the audio" % world,
                           "input_msamples_per_s": bs * nb / ms / 1e3, "channel_msamples_per_s": c["channels"] * bs * nb / ms / 1e3,
-                          "ms_per_step": ms, "buffers_per_step": nb, "scaling": "strong (channels fixed)"}
+                          "ms_per_step": ms, "buffers_per_step": nb, "scaling": "strong (channels fixed)",
+                          "bound": "FMA-heavy (IMAD) pipe", "imad_pipe_frac_est": c["channels"] * bs * nb / (ms * 1e-3) * (3 * 14 + 4) / (imad_peak * world)}
     except Exception as e:  # pragma: no cover
         out["c5_bank"] = {"error": str(e)[:200]}
     if world > 1 or args.no_secondary:
@@ -242,7 +244,8 @@ def secondary_workloads(world, rank, dev, dist, args):
         ms = _time_steps(lambda: ch.process(x, bs), 5, 2, barrier)
         out["c1_int16"] = {"workload": "IQBaseBand<int16> 15 taps, 2.4 MS/s -> 48 kHz + FMDemod, %d buffers of %d" % (nb, bs),
                            "msamples_per_s": bs * nb / ms / 1e3, "ms_per_step": ms,
-                           "algorithmic_gbs": (4 + 2 / 50) * bs * nb / ms / 1e6, "bound": "integer multiply issue (bit-exact path)"}
+                           "algorithmic_gbs": (4 + 2 / 50) * bs * nb / ms / 1e6, "bound": "FMA-heavy (IMAD) pipe (bit-exact path)",
+                           "imad_pipe_frac_est": bs * nb / (ms * 1e-3) * (3 * 14 + 4) / (148 * 64 * 1.965e9)}
     except Exception as e:  # pragma: no cover
         out["c1_int16"] = {"error": str(e)[:200]}
     try:   # C3: FFT-convolution filter, block 4096

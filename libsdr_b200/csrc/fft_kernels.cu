@@ -52,10 +52,13 @@ template <bool INV> __device__ __forceinline__ void dft8(float2 *v) {
   t = v[3]; v[3] = v[6]; v[6] = t;
 }
 
-// Shared-memory index padding: one spare element after every 8 keeps the strided writes of the
-// early stages (stride 8 and 64 elements) off the same banks (8-byte elements, 32 x 4-byte banks).
-__device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
-__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 3) + 8; }
+// Shared-memory index padding: one spare element after every 16 (= one 128-byte row of 8-byte
+// elements).  Consecutive reads stay conflict free (an aligned half-warp never straddles a pad),
+// while the stride-8 writes of the first stage spread over all 16 bank pairs (simulated per stage:
+// 1.0 wavefronts per half-warp everywhere except the second stage's writes at 2.0; the unpadded
+// layout costs 8.0 there and a pad every 8 elements makes EVERY read 2-way conflicted).
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 4) + 8; }
 
 // One Stockham stage of radix R over `n` points: src -> dst.  `mul` (optional) is multiplied into
 // the inputs as they are read (the filter's spectrum).
