@@ -572,18 +572,24 @@ int sdrg_stream_default(void **stream) {
 int sdrg_stream_synchronize(void *stream) { SDRG_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return SDRG_OK; }
 
 struct ThreadScratch { void *p = nullptr; size_t cap = 0; int device = -1; ~ThreadScratch() { if (p) cudaFree(p); } };
-static thread_local ThreadScratch g_scratch;
+// slot 0: the caller's scratch (sdrg_scratch); slot 1: the library's own staging of aliased
+// (in-place) results -- kept apart so that an input staged in slot 0 is never overwritten by it
+static thread_local ThreadScratch g_scratch[2];
+static int scratch_slot(int slot, size_t bytes, void **dev_ptr) {
+  ThreadScratch &sc = g_scratch[slot];
+  if (sc.device != g_device || sc.cap < bytes) {
+    SDRG_CUDA(cudaSetDevice(g_device));
+    if (sc.p) { SDRG_CUDA(cudaDeviceSynchronize()); cudaFree(sc.p); sc.p = nullptr; sc.cap = 0; }
+    const size_t want = bytes < 65536 ? 65536 : bytes + bytes / 2;
+    SDRG_CUDA(cudaMalloc(&sc.p, want));
+    sc.cap = want; sc.device = g_device;
+  }
+  *dev_ptr = sc.p;
+  return SDRG_OK;
+}
 int sdrg_scratch(size_t bytes, void **dev_ptr) {
   if (!dev_ptr) return set_error(SDRG_ERR_ARG, "null argument");
-  if (g_scratch.device != g_device || g_scratch.cap < bytes) {
-    SDRG_CUDA(cudaSetDevice(g_device));
-    if (g_scratch.p) { SDRG_CUDA(cudaDeviceSynchronize()); cudaFree(g_scratch.p); g_scratch.p = nullptr; g_scratch.cap = 0; }
-    const size_t want = bytes < 65536 ? 65536 : bytes + bytes / 2;
-    SDRG_CUDA(cudaMalloc(&g_scratch.p, want));
-    g_scratch.cap = want; g_scratch.device = g_device;
-  }
-  *dev_ptr = g_scratch.p;
-  return SDRG_OK;
+  return scratch_slot(0, bytes, dev_ptr);
 }
 int sdrg_memcpy_h2d_async(void *d_dst, const void *h_src, size_t bytes, void *stream) {
   if (bytes) SDRG_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -943,7 +949,7 @@ static int envelope_dev(bool usb, int scalar, const void *d_in, size_t n, void *
   void *dst = d_out;
   const size_t ob = scalar_bytes(scalar);
   if (d_in == d_out && n) {       // in-place use (demod.hh:68, 145-147): result aside, then over the input
-    int rc = sdrg_scratch(n * ob, &dst);
+    int rc = scratch_slot(1, n * ob, &dst);
     if (rc) return rc;
   }
   int rc = usb ? launch_usbdemod(scalar, d_in, n, dst, (cudaStream_t)stream) : launch_amdemod(scalar, d_in, n, dst, (cudaStream_t)stream);

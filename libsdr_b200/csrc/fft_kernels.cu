@@ -261,10 +261,11 @@ __global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
 int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st) {
   if (batch == 0) return SDRG_OK;
   const size_t smem = (size_t)2 * padded_len(n) * sizeof(float2);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  static size_t attr[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > attr[dev]) {
     SDRG_CUDA(cudaFuncSetAttribute(fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr[dev] = smem;
   }
   int threads = n / 8; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
   fft_batch_kernel<<<(unsigned)batch, threads, smem, st>>>((const float2 *)in, (float2 *)out, n, log2n, inverse, (const float2 *)tw);
@@ -276,18 +277,19 @@ int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
   if (n_blocks == 0) return SDRG_OK;
   const int n = 2 * a.block;
   const size_t smem = (size_t)3 * padded_len(n) * sizeof(float2);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  static size_t attr[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > attr[dev]) {
     SDRG_CUDA(cudaFuncSetAttribute(filter_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr[dev] = smem;
   }
   int threads = n / 8; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
   if (a.n_filters == 1 && n >= 512) {          // one filter: in-place stages on a single buffer (n == 16 * threads)
     const size_t smem1 = (size_t)padded_len(n) * sizeof(float2);
-    static size_t attr1 = 0;
-    if (smem1 > 48 * 1024 && smem1 > attr1) {
+    static size_t attr1[kMaxDevices] = {0};
+    if (smem1 > 48 * 1024 && smem1 > attr1[dev]) {
       SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-      attr1 = smem1;
+      attr1[dev] = smem1;
     }
     filter_ola1_kernel<<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
     SDRG_CHECK_LAUNCH("filter_ola1_kernel");

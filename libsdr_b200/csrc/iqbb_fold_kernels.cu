@@ -367,16 +367,17 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   a.chunks_per_warp = 0;
   static const int pf = [] { const char *e = getenv("SDRG_FOLD_PF"); return e ? atoi(e) : 0; }();   // measured: no gain with round-robin chunks
   a.pf_dist = (uint32_t)pf;
-  static int resident = 0;     // CTAs that fit the device at once: SMs x occupancy
+  static int resident_dev[kMaxDevices] = {0};     // CTAs that fit the device at once: SMs x occupancy
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
-  if (!resident) {
+  const int dev = current_device();
+  if (!resident_dev[dev]) {
     SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 0, per_sm = 0;
-    SDRG_CUDA(cudaGetDevice(&dev));
+    int sms = 0, per_sm = 0;
     SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_f32_kernel, kFoldThreads, smem));
-    resident = sms * (per_sm > 0 ? per_sm : 1);
+    resident_dev[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
+  const int resident = resident_dev[dev];
   const uint64_t want = (n_chunks + kFoldWarps - 1) / kFoldWarps;
   const unsigned grid = (unsigned)(want < (uint64_t)resident ? want : (uint64_t)resident);
   iqbb_fold_f32_kernel<<<grid, kFoldThreads, smem, st>>>(a);
@@ -385,11 +386,12 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
 }
 
 static int launch_fold_tma(IqbbFoldArgs a, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set[kMaxDevices] = {false};
   const size_t smem = (size_t)kFoldWarps * kTmaRing * sizeof(float2);
-  if (!attr_set) {
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   // one contiguous 2 KB-aligned segment per warp; ~2 waves of 148 x 3 CTAs
   const uint64_t target_warps = 148ull * 3 * kFoldWarps * 2;

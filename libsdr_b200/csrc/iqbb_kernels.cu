@@ -351,15 +351,15 @@ int launch_fixed(const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned n_tiles,
   constexpr int NV = (LP + 7 + 3) / 4;
   constexpr int xs_pitch = (kTile + 4 * NV + 8 + 3) & ~3;
   const size_t smem = sizeof(int2) * 128 + sizeof(int2) * kR * kZRow + sizeof(uint32_t) * 2 * xs_pitch;
-  static int resident = 0;               // per instantiation: CTAs that fit the device at once
-  if (!resident) {
-    int dev = 0, sms = 0, per_sm = 0;
-    SDRG_CUDA(cudaGetDevice(&dev));
+  static int resident_dev[kMaxDevices] = {0};      // per instantiation and device: CTAs that fit at once
+  const int dev = current_device();
+  if (!resident_dev[dev]) {
+    int sms = 0, per_sm = 0;
     SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_accum_int_fixed_kernel<LP, IS_S8>, kT, smem));
-    resident = sms * (per_sm > 0 ? per_sm : 1);
+    resident_dev[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
-  const unsigned grid = n_tiles < (unsigned)resident ? n_tiles : (unsigned)resident;
+  const unsigned grid = n_tiles < (unsigned)resident_dev[dev] ? n_tiles : (unsigned)resident_dev[dev];
   iqbb_accum_int_fixed_kernel<LP, IS_S8><<<grid, kT, smem, st>>>(a, taps);
   SDRG_CHECK_LAUNCH("iqbb_accum_int_fixed_kernel");
   return SDRG_OK;

@@ -121,6 +121,26 @@ int main() {
     try { feed.connect(&baseband, true); } catch (ConfigError &) { threw = true; }
     CHECK(threw);
   }
+  {   // (4) small heap-backed buffers (no device mirror) through in-place AM / USB / FM nodes: the input is
+      //     staged in scratch memory and the aliased result must not clobber it before it is read
+    const size_t n = 300;
+    std::vector<int16_t> want_am(n), want_usb(n), want_fm(n);
+    orc_amdemod_s16((const int16_t *)&x[0], n, want_am.data()); orc_usbdemod_s16((const int16_t *)&x[0], n, want_usb.data());
+    int16_t last = 0; want_fm[0] = x[0].real(); orc_fmdemod_s16((const int16_t *)&x[0], n, want_fm.data(), &last);
+    Feed feed; AMDemod<int16_t> am; USBDemod<int16_t> usb; FMDemod<int16_t> fm;
+    Capture<int16_t> c_am, c_usb, c_fm;
+    Feed f_am, f_usb, f_fm;
+    f_am.connect(&am, true); am.connect(&c_am, true);
+    f_usb.connect(&usb, true); usb.connect(&c_usb, true);
+    f_fm.connect(&fm, true); fm.connect(&c_fm, true);
+    f_am.setup(8000.0, n); f_usb.setup(8000.0, n); f_fm.setup(8000.0, n);
+    Buffer<cs16> w1(n), w2(n), w3(n);                   // 1200 bytes each: heap storage
+    CHECK(!w1.isDeviceBacked());
+    memcpy(w1.data(), &x[0], n * sizeof(cs16)); memcpy(w2.data(), &x[0], n * sizeof(cs16)); memcpy(w3.data(), &x[0], n * sizeof(cs16));
+    f_am.push(w1, true); f_usb.push(w2, true); f_fm.push(w3, true);
+    CHECK(c_am.data == want_am); CHECK(c_usb.data == want_usb); CHECK(c_fm.data == want_fm);
+    w1.unref(); w2.unref(); w3.unref();
+  }
   std::printf(failures ? "chain_test: %d FAILED\n" : "chain_test: ok\n", failures);
   return failures ? 1 : 0;
 }
