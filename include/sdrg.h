@@ -90,6 +90,11 @@ typedef struct sdrg_iqbb sdrg_iqbb;
 
 int sdrg_iqbb_create(int scalar, double Fc, double Ff, double width, size_t order,
                      size_t sub_sample, double oFs, sdrg_iqbb **h);   /* ctor, baseband.hh:47-57 */
+/* Real-input BaseBand<int16_t>(Fc, Ff, width, order, sub_sample) (src/baseband.hh:304-529): the same
+ * handle type and process calls, input elements are REAL int16 samples (SDRG_T_S16, 2 bytes each), output
+ * complex int16.  FIR gain 2^16, windows of exactly sub_sample samples, rates kept in double. */
+int sdrg_iqbb_create_real(int scalar, double Fc, double Ff, double width, size_t order,
+                          size_t sub_sample, sdrg_iqbb **h);           /* ctor, baseband.hh:339-350 */
 int sdrg_iqbb_destroy(sdrg_iqbb *h);
 int sdrg_iqbb_set_center_frequency(sdrg_iqbb *h, double Fc);          /* baseband.hh:84-86  */
 int sdrg_iqbb_set_filter_frequency(sdrg_iqbb *h, double Ff);          /* baseband.hh:91-93  */

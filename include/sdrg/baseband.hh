@@ -120,5 +120,62 @@ protected:
   Buffer<CScalar> _buffer;
 };
 
+
+/** Real-input BaseBand<Scalar> (src/baseband.hh:304-529): complex band-pass FIR on a real stream, NCO,
+ * averaging decimator; always out of place into the node's own buffer (baseband.hh:407-418).  Only
+ * Scalar = int16_t is built by libsdrg (sdrg_iqbb_create_real); bit-exact w.r.t. the reference. */
+template <class Scalar>
+class BaseBand : public Sink<Scalar>, public Source {
+public:
+  typedef std::complex<Scalar> CScalar;
+
+  BaseBand(double Fc, double width, size_t order, size_t sub_sample) : _h(0) {            // Ff = Fc, baseband.hh:322
+    gpu::check(sdrg_iqbb_create_real(Traits<Scalar>::scalarId, Fc, Fc, width, order, sub_sample, &_h));
+  }
+  BaseBand(double Fc, double Ff, double width, size_t order, size_t sub_sample) : _h(0) {
+    gpu::check(sdrg_iqbb_create_real(Traits<Scalar>::scalarId, Fc, Ff, width, order, sub_sample, &_h));
+  }
+  virtual ~BaseBand() { sdrg_iqbb_destroy(_h); _buffer.unref(); }
+
+  /** FreqShiftBase interface (src/freqshift.hh:44-65); sampleRate() is Source's, the OUTPUT rate (the
+   * reference's BaseBand inherits two sampleRate() members and cannot be asked without qualification). */
+  double inputSampleRate() const { return _src.sampleRate(); }
+  void setFrequencyShift(double F) { gpu::check(sdrg_iqbb_set_center_frequency(_h, F)); }
+  virtual bool acceptsDeviceBuffers() const { return true; }
+
+  virtual void config(const Config &src_cfg) {
+    const sdrg_config in = src_cfg.c();
+    sdrg_config out;
+    gpu::check(sdrg_iqbb_configure(_h, &in, &out));   // ConfigError "Can not configure BaseBand: Invalid type ..."
+    if (SDRG_T_UNDEFINED == out.type) return;         // incomplete config: ignored (baseband.hh:361)
+    _src = src_cfg;
+    _buffer.unref();
+    _buffer = Buffer<CScalar>(out.buffer_size, 0, true);
+    LogMessage msg(LOG_DEBUG);
+    msg << "Configured BaseBand node (B200):" << std::endl
+        << " sample-rate " << src_cfg.sampleRate() << "Hz" << std::endl
+        << " in buffer size " << src_cfg.bufferSize() << std::endl << " out buffer size " << out.buffer_size;
+    Logger::get().log(msg);
+    this->setConfig(Config::from(out));
+  }
+
+  virtual void process(const Buffer<Scalar> &buffer, bool /*allow_overwrite*/) {
+    if (!_buffer.isUnused()) return;                  // dropped, like the reference (baseband.hh:409-417)
+    void *st = gpu::stream();
+    const void *d_in = gpu::deviceInput(buffer, st);
+    size_t n_out = 0;
+    void *d_out = gpu::deviceOutput(_buffer);
+    if (!d_out) { RuntimeError err; err << "BaseBand: output buffer has no device storage"; throw err; }
+    gpu::check(sdrg_iqbb_process_dev(_h, d_in, buffer.size(), d_out, _buffer.size(), &n_out, st));
+    if (n_out) gpu::publish(_buffer, n_out * sizeof(CScalar), st);
+    this->send(_buffer.head(n_out), true);
+  }
+
+protected:
+  sdrg_iqbb *_h;
+  Config _src;
+  Buffer<CScalar> _buffer;
+};
+
 }  // namespace sdr
 #endif

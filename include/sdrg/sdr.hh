@@ -13,4 +13,5 @@
 #include "autocast.hh"
 #include "fftplan.hh"
 #include "filternode.hh"
+#include "wavfile.hh"
 #endif

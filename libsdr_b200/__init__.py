@@ -9,7 +9,7 @@ from . import synth  # noqa: F401  (host-side synthetic workloads, numpy only)
 
 def __getattr__(name):
     # node classes are resolved lazily so that `import libsdr_b200.synth` works without the .so
-    if name in ("IQBaseBand", "FMDemod", "AMDemod", "USBDemod", "RxChain", "FFTPlan", "FilterNode", "ChannelBank", "Config", "ConfigError"):
+    if name in ("IQBaseBand", "BaseBand", "FMDemod", "AMDemod", "USBDemod", "RxChain", "FFTPlan", "FilterNode", "ChannelBank", "Config", "ConfigError"):
         from . import nodes
         return getattr(nodes, name)
     raise AttributeError(name)

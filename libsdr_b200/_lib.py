@@ -70,6 +70,7 @@ SIGNATURES = {
     "sdrg_memcpy_h2d_async": [_V, _V, _SZ, _V],
     "sdrg_memcpy_d2h_async": [_V, _V, _SZ, _V],
     "sdrg_iqbb_create": [_I, _D, _D, _D, _SZ, _SZ, _D, _PV],
+    "sdrg_iqbb_create_real": [_I, _D, _D, _D, _SZ, _SZ, _PV],
     "sdrg_iqbb_destroy": [_V],
     "sdrg_iqbb_set_center_frequency": [_V, _D],
     "sdrg_iqbb_set_filter_frequency": [_V, _D],

@@ -105,7 +105,9 @@ struct sdrg_iqbb {
   uint32_t taps_len = 1, hist_len = 0;
   std::vector<int32_t> host_taps;      // int paths: the Gauss-form taps as uploaded
   // folded float path (iqbb_fold_kernels.cu)
-  int in_fmt = 0;                      // int16 only: 0 native, 2 complex uint8, 3 complex int8 (fused AutoCast)
+  int in_fmt = 0;                      // int16 only: 0 native, 2 complex uint8, 3 complex int8 (fused AutoCast), 4 real int16
+  bool real_input = false;             // BaseBand<int16_t> (src/baseband.hh:304-529): real stream, plain windows, 2^16 FIR gain
+  double r_Ff = 0, r_width = 0, r_Fs = 0;   // its double members _Ff, _width and FreqShiftBase::_Fs
   int float_path = 0;                  // 0 auto, 1 direct, 2 folded
   bool fold = false;
   void *d_tab_a = nullptr, *d_tab_u = nullptr;
@@ -150,7 +152,15 @@ size_t audio_bytes(int scalar, int demod) {
 }
 
 size_t in_sample_bytes(const sdrg_iqbb *h) { return h->in_fmt ? 2 : sample_bytes(h->d.scalar); }
-int input_type_of(const sdrg_iqbb *h) { return h->in_fmt == 2 ? SDRG_T_CU8 : (h->in_fmt == 3 ? SDRG_T_CS8 : complex_type_of(h->d.scalar)); }
+int input_type_of(const sdrg_iqbb *h) {
+  if (h->real_input) return h->d.scalar;
+  return h->in_fmt == 2 ? SDRG_T_CU8 : (h->in_fmt == 3 ? SDRG_T_CS8 : complex_type_of(h->d.scalar));
+}
+const char *node_name(const sdrg_iqbb *h) { return h->real_input ? "BaseBand" : "IQBaseBand"; }
+void design_filter(sdrg_iqbb *h) {
+  if (h->real_input) design_kernel_real(h->d, h->r_Ff, h->r_width, h->r_Fs);
+  else design_kernel(h->d);
+}
 
 int grow(void **p, size_t *cap, size_t need) {
   if (*cap >= need && *p) return SDRG_OK;
@@ -165,7 +175,9 @@ int grow(void **p, size_t *cap, size_t need) {
 void free_dev(void **p) { if (*p) { cudaFree(*p); *p = nullptr; } }
 
 typedef WindowAdvance Advance;
-Advance advance(const sdrg_iqbb *h, uint64_t n) { return window_advance(h->consumed, h->d.sub_sample, n); }
+Advance advance(const sdrg_iqbb *h, uint64_t n) {
+  return h->real_input ? window_advance_plain(h->consumed, h->d.sub_sample, n) : window_advance(h->consumed, h->d.sub_sample, n);
+}
 
 // Folded float path: A(a) and U(r,e) in double on the host (see iqbb_fold_kernels.cu).
 int upload_fold_tables(sdrg_iqbb *h) {
@@ -282,18 +294,18 @@ void reset_stream_state(sdrg_iqbb *h) {
 // config()-time recomputation (baseband.hh:156-194): host part
 int design_only(sdrg_iqbb *h) {
   IqbbDesign &d = h->d;
-  if (d.oFs > 0) {
+  if (d.oFs > 0 && !h->real_input) {
     d.sub_sample = size_t(d.Fs / d.oFs);
     if (d.sub_sample < 1) d.sub_sample = 1;
   }
   if (d.sub_sample < 1) d.sub_sample = 1;    // the reference would divide by zero
-  if (d.sub_sample > (1u << 30)) return set_error(SDRG_ERR_CONFIG, "IQBaseBand: sub-sampling %zu too large", d.sub_sample);
-  design_kernel(d);
-  h->nco_Fs = double(d.Fs);
+  if (d.sub_sample > (1u << 30)) return set_error(SDRG_ERR_CONFIG, "%s: sub-sampling %zu too large", node_name(h), d.sub_sample);
+  design_filter(h);
+  h->nco_Fs = h->real_input ? h->r_Fs : double(d.Fs);       // BaseBand keeps the double rate (baseband.hh:371)
   design_lut_increment(d, h->nco_Fs);
   d.out_bs = d.source_bs / d.sub_sample;
   if (d.source_bs % d.sub_sample) d.out_bs += 1;
-  d.out_rate = double(size_t(d.Fs) / d.sub_sample);
+  d.out_rate = h->real_input ? h->r_Fs / double(d.sub_sample) : double(size_t(d.Fs) / d.sub_sample);
   return SDRG_OK;
 }
 
@@ -335,6 +347,7 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   a.neg = h->d.negative ? 1u : 0u;
   a.zero_next = h->acc_dirty[q];
   a.in_fmt = (uint32_t)h->in_fmt;
+  a.fir_shift = h->real_input ? 16u : 14u;
   IqbbFinalizeArgs f{};
   f.acc_cur = h->d_acc[p]; f.acc_next = h->d_acc[q];
   f.bb_out = d_bb; f.audio_out = d_audio;
@@ -623,6 +636,22 @@ int sdrg_iqbb_create(int scalar, double Fc, double Ff, double width, size_t orde
   return SDRG_OK;
 }
 
+// BaseBand<Scalar>(Fc, Ff, width, order, sub_sample) on a REAL stream (src/baseband.hh:339-350).  Only
+// int16_t is built (the reference instantiates it nowhere else either: examples/, cmd/ use int16 audio).
+int sdrg_iqbb_create_real(int scalar, double Fc, double Ff, double width, size_t order, size_t sub_sample,
+                          sdrg_iqbb **out) {
+  if (!out) return set_error(SDRG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (scalar != SDRG_T_S16)
+    return set_error(SDRG_ERR_ARG, "BaseBand: unsupported scalar type %s (%d), only int16", type_name(scalar), scalar);
+  int rc = sdrg_iqbb_create(SDRG_T_S16, Fc, Ff, width, order, sub_sample, 0.0, out);
+  if (rc) return rc;
+  sdrg_iqbb *h = *out;
+  h->real_input = true; h->in_fmt = 4;
+  h->r_Ff = Ff; h->r_width = width;
+  return SDRG_OK;
+}
+
 int sdrg_iqbb_destroy(sdrg_iqbb *h) {
   if (!h) return SDRG_OK;
   cudaSetDevice(h->device);
@@ -644,10 +673,10 @@ static int refresh_kernel(sdrg_iqbb *h) {
   SDRG_CUDA(cudaSetDevice(h->device));
   SDRG_CUDA(cudaDeviceSynchronize());
   const uint32_t old_hist = h->hist_len;
-  design_kernel(h->d);
+  design_filter(h);
   // the history buffers depend on the stripped tap count; keep them when it is unchanged
   std::vector<char> keep;
-  const size_t sb = sample_bytes(h->d.scalar);
+  const size_t sb = in_sample_bytes(h);
   if (old_hist) { keep.resize(old_hist * sb); SDRG_CUDA(cudaMemcpy(keep.data(), h->d_hist[h->parity], keep.size(), cudaMemcpyDeviceToHost)); }
   int rc = upload_design(h);
   if (rc) return rc;
@@ -662,7 +691,8 @@ static int refresh_kernel(sdrg_iqbb *h) {
 int sdrg_iqbb_set_center_frequency(sdrg_iqbb *h, double Fc) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   h->d.Fc = int32_t(Fc);
-  h->d.freq_shift = double(h->d.Fc);       // setFrequencyShift(_Fc) receives the int32 member
+  h->d.freq_shift = h->real_input ? Fc     // FreqShiftBase::setFrequencyShift(double), freqshift.hh:62-65
+                                  : double(h->d.Fc);   // IQBaseBand: setFrequencyShift(_Fc) receives the int32 member
   design_lut_increment(h->d, h->nco_Fs);
   h->phase0 = 0;                           // _lut_count = 0
   if (h->configured && h->d.scalar == SDRG_T_F32) {   // the folded tables embed the NCO increment
@@ -674,12 +704,12 @@ int sdrg_iqbb_set_center_frequency(sdrg_iqbb *h, double Fc) {
 }
 int sdrg_iqbb_set_filter_frequency(sdrg_iqbb *h, double Ff) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
-  h->d.Ff = int32_t(Ff);
+  h->d.Ff = int32_t(Ff); h->r_Ff = Ff;
   return refresh_kernel(h);
 }
 int sdrg_iqbb_set_filter_width(sdrg_iqbb *h, double width) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
-  h->d.width = int32_t(width);
+  h->d.width = int32_t(width); h->r_width = width;
   return refresh_kernel(h);
 }
 int sdrg_iqbb_set_order(sdrg_iqbb *h, size_t order) {
@@ -689,7 +719,7 @@ int sdrg_iqbb_set_order(sdrg_iqbb *h, size_t order) {
   if (!h->configured) return SDRG_OK;
   SDRG_CUDA(cudaSetDevice(h->device));
   SDRG_CUDA(cudaDeviceSynchronize());
-  design_kernel(h->d);
+  design_filter(h);
   return upload_design(h);                 // fresh, zeroed history (the reference leaves it uninitialised)
 }
 int sdrg_iqbb_set_subsample(sdrg_iqbb *h, size_t sub_sample) {
@@ -702,6 +732,7 @@ int sdrg_iqbb_set_subsample(sdrg_iqbb *h, size_t sub_sample) {
 }
 int sdrg_iqbb_set_output_sample_rate(sdrg_iqbb *h, double oFs) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (h->real_input) return set_error(SDRG_ERR_CONFIG, "BaseBand: no output-rate setter (src/baseband.hh:304-529), use the sub-sampling");
   h->d.oFs = oFs;
   if (h->d.Fs == 0 || h->d.source_bs == 0) return SDRG_OK;
   SDRG_CUDA(cudaSetDevice(h->device));
@@ -712,6 +743,11 @@ int sdrg_iqbb_set_output_sample_rate(sdrg_iqbb *h, double oFs) {
 int sdrg_iqbb_set_input_type(sdrg_iqbb *h, int type) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: select the input type before config()");
+  if (h->real_input) {
+    if (type == h->d.scalar) return SDRG_OK;
+    return set_error(SDRG_ERR_CONFIG, "Can not configure BaseBand: Invalid type %s (%d), expected %s (%d)", type_name(type), type,
+                     type_name(h->d.scalar), h->d.scalar);
+  }
   if (type == complex_type_of(h->d.scalar)) { h->in_fmt = 0; return SDRG_OK; }
   if (h->d.scalar != SDRG_T_S16 || (type != SDRG_T_CU8 && type != SDRG_T_CS8))
     return set_error(SDRG_ERR_CONFIG, "AutoCast: Can not cast from type %s (%d) to %s (%d)", type_name(type), type,
@@ -732,11 +768,11 @@ int sdrg_iqbb_configure(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out) 
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
   bool skip = false;
-  int rc = config_common("IQBaseBand", input_type_of(h), src, true, &skip);
+  int rc = config_common(node_name(h), input_type_of(h), src, true, &skip);
   if (rc || skip) return rc;
   SDRG_CUDA(cudaSetDevice(h->device));
   SDRG_CUDA(cudaDeviceSynchronize());
-  h->d.Fs = int32_t(src->sample_rate);
+  h->d.Fs = int32_t(src->sample_rate); h->r_Fs = src->sample_rate;
   h->d.source_bs = src->buffer_size;
   rc = reconfigure(h);
   if (rc) return rc;
@@ -753,9 +789,9 @@ int sdrg_iqbb_design(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (out) { out->type = SDRG_T_UNDEFINED; out->sample_rate = 0; out->buffer_size = 0; out->num_buffers = 0; }
   bool skip = false;
-  int rc = config_common("IQBaseBand", input_type_of(h), src, true, &skip);
+  int rc = config_common(node_name(h), input_type_of(h), src, true, &skip);
   if (rc || skip) return rc;
-  h->d.Fs = int32_t(src->sample_rate);
+  h->d.Fs = int32_t(src->sample_rate); h->r_Fs = src->sample_rate;
   h->d.source_bs = src->buffer_size;
   h->configured = false;                    // tables are not on the device
   rc = design_only(h);

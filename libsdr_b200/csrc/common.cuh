@@ -73,6 +73,7 @@ static const size_t kMaxOrder = 1024;
 void design_lut(IqbbDesign &d);
 void design_kernel(IqbbDesign &d);
 void design_lut_increment(IqbbDesign &d, double nco_Fs);
+void design_kernel_real(IqbbDesign &d, double Ff, double width, double Fs);   // BaseBand<int16_t>, 2^16 scaled
 
 // Window grid in closed form.  With c = samples consumed since config(), global
 // sample n carries the window counter q(n) = max(n,1)-1 (window 0 holds ss+1 samples because
@@ -88,6 +89,17 @@ static inline WindowAdvance window_advance(uint64_t c, uint64_t ss, uint64_t n) 
   a.r0 = c ? (uint32_t)((c - 1) % ss) : 0u;
   const uint64_t lo = c ? c : 1;                           // first global index that can complete
   a.e0 = (uint32_t)(((lo + ss - 1) / ss) * ss - c);
+  return a;
+}
+
+// Real-input BaseBand (src/baseband.hh:425-436): the counter is incremented BEFORE the test, so every
+// window holds exactly ss samples and global sample n completes one when (n+1) % ss == 0.
+static inline WindowAdvance window_advance_plain(uint64_t c, uint64_t ss, uint64_t n) {
+  WindowAdvance a{};
+  a.n_out = (c + n) / ss - c / ss;
+  a.first = 0;
+  a.r0 = (uint32_t)(c % ss);
+  a.e0 = (uint32_t)(ss - 1 - c % ss);
   return a;
 }
 

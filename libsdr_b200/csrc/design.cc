@@ -64,6 +64,32 @@ void design_kernel(IqbbDesign &d) {
   }
 }
 
+// BaseBand<Scalar>::_update_filter_kernel (src/baseband.hh:462-487): centre tap 1, exp(+j..) shift,
+// Blackman window over (i+1)/(order+2), gain 2^Traits<Scalar>::shift; Ff, width and Fs are doubles here.
+void design_kernel_real(IqbbDesign &d, double Ff, double width, double Fs) {
+  const size_t L = d.order;
+  std::complex<double> a[kMaxOrder];
+  const double w = (2 * M_PI * width) / (2 * Fs);
+  const double M = double(L) / 2;
+  double norm = 0;
+  for (size_t i = 0; i < L; ++i) {
+    if (L == 2 * i) a[i] = 1;
+    else a[i] = std::sin(w * (i - M)) / (w * (i - M));
+  }
+  for (size_t i = 0; i < L; ++i) {
+    a[i] = a[i] * std::exp(std::complex<double>(0, (2 * M_PI * Ff * i) / Fs));
+    a[i] *= (0.42 - 0.5 * cos((2 * M_PI * (i + 1)) / (L + 2)) + 0.08 * cos((4 * M_PI * (i + 1)) / (L + 2)));
+    norm += std::abs(a[i]);
+  }
+  for (size_t i = 0; i < L; ++i) {
+    const std::complex<double> q = (double(1 << trait_shift(d.scalar)) * a[i]) / norm;
+    d.k_re[i] = int32_t(q.real());
+    d.k_im[i] = int32_t(q.imag());
+    d.kd_re[i] = a[i].real() / norm;
+    d.kd_im[i] = a[i].imag() / norm;
+  }
+}
+
 const char *type_name(int type) {
   static const char *names[] = {"UNDEFINED", "uint8", "int8", "uint16", "int16", "float", "double",
                                 "complex uint8", "complex int8", "complex uint16", "complex int16",

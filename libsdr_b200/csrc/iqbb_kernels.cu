@@ -42,6 +42,7 @@ __device__ __forceinline__ void unpack16(uint32_t v, int &re, int &im) {
 // through an int8_t pointer, (v - 127) << 8 (reference quirk), resp. complex int8, v << 8.
 __device__ __forceinline__ uint32_t load_cs16(const void *base, int64_t idx, uint32_t fmt) {
   if (fmt == 0) return ((const uint32_t *)base)[idx];
+  if (fmt == 4) return (uint32_t)((const uint16_t *)base)[idx];      // real input: imaginary part 0
   const char2 s = ((const char2 *)base)[idx];
   const int bias = fmt == 2 ? 127 : 0;
   const uint32_t re = (uint32_t)(uint16_t)(int16_t)(((int)s.x - bias) << 8);
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs 
   const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
-    int yr = ((int)(A1[r] - A3[r])) >> 14;
-    int yi = ((int)(A1[r] + A2[r])) >> 14;
+    int yr = ((int)(A1[r] - A3[r])) >> a.fir_shift;
+    int yi = ((int)(A1[r] + A2[r])) >> a.fir_shift;
     if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }   // narrowed to complex<int16_t> on the call
     if (a.nco) {
       const uint32_t ph = (a.phase0 + (i0 + r) * a.inc) & 0x7fffu;
@@ -328,8 +329,8 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccu
     uint32_t ph = (a.phase0 + i0 * a.inc) & 0x7fffu;
 #pragma unroll
     for (int r = 0; r < kR; ++r) {
-      int yr = ((int)(A1[r] - A3[r])) >> 14;
-      int yi = ((int)(A1[r] + A2[r])) >> 14;
+      int yr = ((int)(A1[r] - A3[r])) >> a.fir_shift;
+      int yi = ((int)(A1[r] + A2[r])) >> a.fir_shift;
       if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }
       if (a.nco) {
         const int2 l = lut[(ph >> 8) ^ negx];

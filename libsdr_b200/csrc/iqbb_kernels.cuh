@@ -30,7 +30,9 @@ struct IqbbAccumArgs {
   uint32_t    nco;        // 0: lut_inc == 0, the mixer is bypassed entirely (freqshift.hh:61)
   uint32_t    neg;        // negative frequency shift: idx = 127 - idx
   uint32_t    zero_next;
-  uint32_t    in_fmt;     // int16 path only: 0 = complex<int16_t> input, 2 = complex uint8, 3 = complex int8 (fused AutoCast)
+  uint32_t    in_fmt;     // int16 path only: 0 = complex<int16_t> input, 2 = complex uint8, 3 = complex int8 (fused AutoCast),
+                          // 4 = REAL int16 (BaseBand<int16_t>, src/baseband.hh:304): sample = (x, 0)
+  uint32_t    fir_shift;  // integer paths: the FIR result is shifted right by this (14 IQBaseBand, 16 BaseBand)
 };
 
 // One process() call of the folded float kernel (iqbb_fold_kernels.cu)

@@ -49,6 +49,8 @@ class IQBaseBand:
     """IQBaseBand<Scalar>(Fc, Ff, width, order, sub_sample, oFs=0)  (src/baseband.hh:47-57).
     The 5-argument reference constructor (Ff = Fc, baseband.hh:35) is `IQBaseBand(scalar, Fc, None, ...)`."""
 
+    _in_shape = (-1, 2)
+
     def __init__(self, scalar, Fc, Ff, width, order, sub_sample, oFs=0.0):
         self.scalar = scalar_id(scalar)
         self.dtype = _NP[self.scalar]
@@ -136,12 +138,35 @@ class IQBaseBand:
             _lib.call("sdrg_iqbb_process_dev", self._h, C.c_void_p(x.data_ptr()), n_in,
                       C.c_void_p(out.data_ptr()), n_out, C.byref(got), _stream_ptr())
             return out[:got.value]
-        x = np.ascontiguousarray(x, dtype=getattr(self, "in_dtype", self.dtype)).reshape(-1, 2)
+        x = np.ascontiguousarray(x, dtype=getattr(self, "in_dtype", self.dtype)).reshape(self._in_shape)
         n_out = self.outputs_for(x.shape[0])
         out = np.zeros((n_out, 2), dtype=self.dtype)
         got = C.c_size_t(0)
         _lib.call("sdrg_iqbb_process", self._h, _np_ptr(x), x.shape[0], _np_ptr(out), n_out, C.byref(got))
         return out[:got.value]
+
+
+class BaseBand(IQBaseBand):
+    """BaseBand<int16_t>(Fc, Ff, width, order, sub_sample) on a REAL int16 stream (src/baseband.hh:304-529):
+    complex band-pass FIR (gain 2^16) -> NCO -> mean of exactly sub_sample samples; output (n, 2) int16.
+    The 4-argument reference constructor (Ff = Fc, baseband.hh:322) is `BaseBand(Fc, None, ...)`."""
+
+    _in_shape = (-1,)
+
+    def __init__(self, Fc, Ff, width, order, sub_sample):
+        self.scalar = _lib.T_S16
+        self.dtype = np.int16
+        self._in_type = _lib.T_S16
+        self._h = C.c_void_p()
+        if Ff is None:
+            Ff = Fc
+        _lib.call("sdrg_iqbb_create_real", self.scalar, float(Fc), float(Ff), float(width), int(order),
+                  int(sub_sample), C.byref(self._h))
+        self.out_config = Config()
+
+    def setFrequencyShift(self, Fc):
+        """FreqShiftBase::setFrequencyShift (src/freqshift.hh:62-65)."""
+        _lib.call("sdrg_iqbb_set_center_frequency", self._h, float(Fc))
 
 
 class FMDemod:
@@ -375,6 +400,8 @@ class FilterNode:
 class ChannelBank:
     """C independent IQBaseBand<Scalar>(Fc[c], Ff[c], width, order, sub_sample, oFs) nodes on one input
     stream, each with FM/AM/USB demodulators connected out of place (sdrg_bank_*)."""
+
+    _in_shape = (-1, 2)
 
     def __init__(self, scalar, Fc, Ff, width, order, sub_sample, oFs=0.0):
         self.scalar = scalar_id(scalar)

@@ -123,6 +123,9 @@ class IQBaseBand:
     @property
     def out_rate(self): return self.s.out_rate
 
+    def set_frequency_shift(self, Fc):
+        _lib.orc_rbb_set_frequency_shift(C.byref(self.s), Fc)
+
     def kernel_i32(self):
         L = self.s.order
         return np.stack([np.array(self.s.kr[:L], dtype=np.int32), np.array(self.s.ki[:L], dtype=np.int32)], axis=1)
@@ -133,6 +136,45 @@ class IQBaseBand:
 
     def lut_i32(self):
         return np.stack([np.array(self.s.lut_r[:], dtype=np.int32), np.array(self.s.lut_i[:], dtype=np.int32)], axis=1)
+
+
+_lib.orc_rbb_init.argtypes = [C.POINTER(_IQBB), C.c_double, C.c_double, C.c_double, C.c_size_t, C.c_size_t]
+_lib.orc_rbb_config.argtypes = [C.POINTER(_IQBB), C.c_double, C.c_size_t]
+_lib.orc_rbb_config.restype = C.c_int
+_lib.orc_rbb_set_frequency_shift.argtypes = [C.POINTER(_IQBB), C.c_double]
+_lib.orc_rbb_process.argtypes = [C.POINTER(_IQBB), C.c_void_p, C.c_size_t, C.c_void_p]
+_lib.orc_rbb_process.restype = C.c_size_t
+
+
+class BaseBand:
+    """Oracle real-input BaseBand<int16_t> (src/baseband.hh:304-529): real int16 in, (n,2) int16 out."""
+
+    def __init__(self, Fc, Ff, width, order, sub_sample):
+        self.s = _IQBB()
+        _lib.orc_rbb_init(C.byref(self.s), Fc, Ff, width, order, sub_sample)
+
+    def config(self, sample_rate, buffer_size):
+        return _lib.orc_rbb_config(C.byref(self.s), sample_rate, buffer_size)
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, dtype=np.int16).reshape(-1)
+        out = np.zeros((x.shape[0] // max(1, self.s.sub_sample) + 2, 2), dtype=np.int16)
+        n = _lib.orc_rbb_process(C.byref(self.s), _p(x), x.shape[0], _p(out))
+        return out[:n].copy()
+
+    def set_frequency_shift(self, Fc):
+        _lib.orc_rbb_set_frequency_shift(C.byref(self.s), Fc)
+
+    def kernel_i32(self):
+        L = self.s.order
+        return np.stack([np.array(self.s.kr[:L], dtype=np.int32), np.array(self.s.ki[:L], dtype=np.int32)], axis=1)
+
+    @property
+    def lut_inc(self): return self.s.lut_inc
+    @property
+    def out_rate(self): return self.s.out_rate
+    @property
+    def out_bs(self): return self.s.out_bs
 
 
 class FMDemod:

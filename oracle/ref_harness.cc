@@ -12,6 +12,11 @@
 //   ola <in.bin cf32> <block> <Fs> <fmin> <fmax> <prefix>
 //         runs FilterSink<float> -> FilterSource<float> with a double-precision FFTPlan stand-in
 //         (FFTW3 is not installed); writes <prefix>.kern/.taps/.out
+//   rbb <in.bin int16> <buffer_size> <Fs> <Fc> <Ff> <width> <order> <sub_sample> <prefix>
+//         runs the real-input BaseBand<int16_t> (src/baseband.hh:304-529); writes <prefix>.params/.bb/.counts
+//   wav <u8|s16|cu8|cs16> <in.bin> <buffer_size> <Fs> <out.wav> <prefix>
+//         writes the input through WavSink<T> (src/wavfile.hh:16-128), reads it back with WavSource
+//         (src/wavfile.cc); writes <prefix>.data/.counts/.cfg (type, rate, buffer size as 3 doubles)
 //   cast <cu8|cs8> <in.bin> <buffer_size> <prefix>
 //         runs AutoCast< std::complex<int16_t> > on complex 8-bit input; writes <prefix>.cs16
 //   deemph <in.bin int16> <buffer_size> <Fs> <prefix>
@@ -62,6 +67,7 @@ protected:
 #include "demod.hh"
 #include "filternode.hh"
 #include "autocast.hh"
+#include "wavfile.hh"
 
 using namespace sdr;
 
@@ -235,6 +241,79 @@ static int run_ola(char **a) {
   return 0;
 }
 
+struct RBB : public BaseBand<int16_t> {
+  RBB(double Fc, double Ff, double w, size_t o, size_t ss) : BaseBand<int16_t>(Fc, Ff, w, o, ss) {}
+  void dump(FILE *f) {
+    int64_t hdr[4] = { (int64_t)this->_order, (int64_t)this->_sub_sample, (int64_t)FreqShiftBase<int16_t>::_lut_inc,
+                       (int64_t)(0 > FreqShiftBase<int16_t>::_freq_shift) };
+    fwrite(hdr, sizeof(hdr), 1, f);
+    for (size_t i = 0; i < this->_order; i++) {
+      int32_t v[2] = { this->_kernel[i].real(), this->_kernel[i].imag() }; fwrite(v, sizeof(v), 1, f);
+    }
+  }
+};
+
+static int run_rbb(char **a) {
+  std::vector<char> raw = slurp(a[0]);
+  size_t bs = strtoull(a[1], 0, 10);
+  double Fs = atof(a[2]), Fc = atof(a[3]), Ff = atof(a[4]), width = atof(a[5]);
+  size_t order = strtoull(a[6], 0, 10), ss = strtoull(a[7], 0, 10);
+  std::string prefix = a[8];
+  size_t total = raw.size() / sizeof(int16_t);
+  Feed<int16_t> feed; RBB bb(Fc, Ff, width, order, ss); Dump< std::complex<int16_t> > dump;
+  dump.f = wopen(prefix + ".bb");
+  feed.connect(&bb, true); bb.connect(&dump, true);
+  feed.setup(Fs, bs);
+  FILE *fp = wopen(prefix + ".params"); bb.dump(fp); fclose(fp);
+  Buffer<int16_t> work(bs);
+  for (size_t off = 0; off < total; off += bs) {
+    size_t n = std::min(bs, total - off);
+    memcpy(work.data(), raw.data() + off * sizeof(int16_t), n * sizeof(int16_t));
+    feed.push(work.head(n), false);
+  }
+  fclose(dump.f);
+  FILE *fc = wopen(prefix + ".counts"); fwrite(dump.sizes.data(), sizeof(uint32_t), dump.sizes.size(), fc); fclose(fc);
+  return 0;
+}
+
+// Raw capture sink for WavSource (its element type is only known after open()).
+class RawDump : public SinkBase {
+public:
+  RawDump() : f(0) {}
+  virtual void config(const Config &c) { cfg = c; }
+  virtual void handleBuffer(const RawBuffer &b, bool) {
+    fwrite(b.data(), 1, b.bytesLen(), f); sizes.push_back((uint32_t)b.bytesLen());
+  }
+  FILE *f; Config cfg; std::vector<uint32_t> sizes;
+};
+
+template <class T>
+static int run_wav(char **a) {
+  std::vector<char> raw = slurp(a[0]);
+  size_t bs = strtoull(a[1], 0, 10); double Fs = atof(a[2]);
+  std::string wav = a[3], prefix = a[4];
+  size_t total = raw.size() / sizeof(T);
+  {
+    Feed<T> feed; WavSink<T> sink(wav);
+    feed.connect(&sink, true); feed.setup(Fs, bs);
+    Buffer<T> work(bs);
+    for (size_t off = 0; off < total; off += bs) {
+      size_t n = std::min(bs, total - off);
+      memcpy(work.data(), raw.data() + off * sizeof(T), n * sizeof(T));
+      feed.push(work.head(n), false);
+    }
+    sink.close();
+  }
+  WavSource src(wav, bs); RawDump dump; dump.f = wopen(prefix + ".data");
+  src.connect(&dump, true);
+  while (src.isOpen()) src.next();
+  fclose(dump.f);
+  FILE *fc = wopen(prefix + ".counts"); fwrite(dump.sizes.data(), sizeof(uint32_t), dump.sizes.size(), fc); fclose(fc);
+  double cfg[3] = { (double)dump.cfg.type(), dump.cfg.sampleRate(), (double)dump.cfg.bufferSize() };
+  FILE *fg = wopen(prefix + ".cfg"); fwrite(cfg, sizeof(cfg), 1, fg); fclose(fg);
+  return 0;
+}
+
 template <class T>
 static int run_cast(char **a) {
   std::vector<char> raw = slurp(a[0]);
@@ -344,6 +423,14 @@ int main(int argc, char **argv) {
       if (!strcmp(argv[2], "s8")) return run_bb<int8_t, int16_t>(argv + 3);
     } else if (cmd == "ola" && argc == 8) {
       return run_ola(argv + 2);
+    } else if (cmd == "rbb" && argc == 11) {
+      return run_rbb(argv + 2);
+    } else if (cmd == "wav" && argc == 8) {
+      std::string t = argv[2];
+      if (t == "u8") return run_wav<uint8_t>(argv + 3);
+      if (t == "s16") return run_wav<int16_t>(argv + 3);
+      if (t == "cu8") return run_wav< std::complex<uint8_t> >(argv + 3);
+      if (t == "cs16") return run_wav< std::complex<int16_t> >(argv + 3);
     } else if (cmd == "cast" && argc == 6) {
       if (!strcmp(argv[2], "cu8")) return run_cast< std::complex<uint8_t> >(argv + 3);
       if (!strcmp(argv[2], "cs8")) return run_cast< std::complex<int8_t> >(argv + 3);

@@ -245,6 +245,81 @@ size_t orc_iqbb_process(orc_iqbb *s, const void *in, size_t n, void *out) {
   return process_int(s, in, n, out);
 }
 
+/* ---- real-input BaseBand<int16_t> (src/baseband.hh:304-529) --------------------------------- */
+void orc_rbb_init(orc_iqbb *s, double Fc, double Ff, double width, size_t order, size_t sub_sample) {
+  memset(s, 0, sizeof(*s));
+  s->scalar = ORC_S16;
+  s->freq_shift = Fc;
+  s->order = order < 1 ? 1 : order;
+  if (s->order > ORC_MAX_ORDER) s->order = ORC_MAX_ORDER;
+  s->sub_sample = sub_sample;
+  s->kdr[0] = Ff; s->kdr[1] = width;            /* parked here: the design needs the un-truncated values */
+  build_lut(s);
+}
+
+int orc_rbb_config(orc_iqbb *s, double Fs, size_t buffer_size) {
+  if (Fs == 0 || buffer_size == 0) return 1;
+  const double rbb_Ff = s->kdr[0], rbb_width = s->kdr[1];   /* doubles in BaseBand, not int32 like IQBaseBand's */
+  s->nco_Fs = Fs;                                /* setSampleRate(src_cfg.sampleRate()): a double */
+  update_lut_incr(s);
+  /* _update_filter_kernel, baseband.hh:462-487 */
+  {
+    static double ar[ORC_MAX_ORDER], ai[ORC_MAX_ORDER];
+    double w = (2 * M_PI * rbb_width) / (2 * Fs);
+    double M = (double)(s->order) / 2;
+    double norm = 0;
+    for (size_t i = 0; i < s->order; i++) {
+      double a0 = (s->order == (2 * i)) ? 1 : sin(w * (i - M)) / (w * (i - M));
+      double complex e = cexp(CMPLX(0, (2 * M_PI * rbb_Ff * i) / Fs));
+      double re = a0 * creal(e) - 0.0 * cimag(e), im = a0 * cimag(e) + 0.0 * creal(e);
+      double win = (0.42 - 0.5 * cos((2 * M_PI * (i + 1)) / (s->order + 2)) + 0.08 * cos((4 * M_PI * (i + 1)) / (s->order + 2)));
+      re *= win; im *= win;
+      ar[i] = re; ai[i] = im;
+      norm += hypot(re, im);
+    }
+    for (size_t i = 0; i < s->order; i++) {
+      s->kr[i] = (int32_t)(((double)(1 << 16) * ar[i]) / norm);
+      s->ki[i] = (int32_t)(((double)(1 << 16) * ai[i]) / norm);
+    }
+  }
+  s->out_bs = buffer_size / s->sub_sample + ((buffer_size % s->sub_sample) ? 1 : 0);
+  s->out_rate = Fs / (double)s->sub_sample;
+  s->last_r = s->last_i = 0; s->sample_count = 0; s->ring_offset = 0;
+  return 0;
+}
+
+/* FreqShiftBase::setFrequencyShift, src/freqshift.hh:62-65 */
+void orc_rbb_set_frequency_shift(orc_iqbb *s, double Fc) { s->freq_shift = Fc; update_lut_incr(s); }
+
+size_t orc_rbb_process(orc_iqbb *s, const int16_t *in, size_t n, int16_t *out) {
+  size_t j = 0;
+  const size_t L = s->order;
+  for (size_t i = 0; i < n; i++) {
+    s->ring_r[s->ring_offset] = in[i];
+    int32_t fr = 0, fi = 0;
+    size_t idx = s->ring_offset + 1;
+    if (L == idx) idx = 0;
+    for (size_t t = 0; t < L; t++, idx++) {
+      if (L == idx) idx = 0;
+      fr = w32_add(fr, w32_mul(s->kr[t], s->ring_r[idx]));      /* complex<int32> * int32 */
+      fi = w32_add(fi, w32_mul(s->ki[t], s->ring_r[idx]));
+    }
+    fr = asr32(fr, 16); fi = asr32(fi, 16);                      /* >> Traits<int16_t>::shift */
+    nco_s16(s, &fr, &fi);
+    s->last_r = w32_add(s->last_r, fr); s->last_i = w32_add(s->last_i, fi);
+    s->sample_count++;
+    s->ring_offset++;
+    if (L == s->ring_offset) s->ring_offset = 0;
+    if (s->sub_sample == s->sample_count) {
+      int32_t vr = s->last_r, vi = s->last_i;
+      cdiv_ss(&vr, &vi, (int32_t)s->sub_sample);
+      out[2 * j] = (int16_t)vr; out[2 * j + 1] = (int16_t)vi;
+      s->last_r = s->last_i = 0; s->sample_count = 0; j++;
+    }
+  }
+  return j;
+}
+
 /* ---- demodulators ---------------------------------------------------------------------------- */
 
 /* src/math.hh:12-21 and 31-40 (identical bodies once the operands are promoted to int32) */

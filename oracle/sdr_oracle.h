@@ -82,6 +82,15 @@ void orc_usbdemod_s16(const int16_t *in_iq, size_t n, int16_t *out);
 void orc_usbdemod_s8(const int8_t *in_iq, size_t n, int8_t *out);
 void orc_usbdemod_f32(const float *in_iq, size_t n, float *out);
 
+/* Real-input BaseBand<int16_t> (src/baseband.hh:304-529): complex band-pass FIR on a real stream
+ * (kernel scaled 2^16, result >> 16), NCO, averaging decimator with plain ss-sample windows (the
+ * sample counter is incremented BEFORE the test here, baseband.hh:425-436).  Reuses orc_iqbb's state:
+ * ring_r holds the real history, kr/ki the kernel. */
+void orc_rbb_init(orc_iqbb *s, double Fc, double Ff, double width, size_t order, size_t sub_sample);
+int  orc_rbb_config(orc_iqbb *s, double sample_rate, size_t buffer_size);
+void orc_rbb_set_frequency_shift(orc_iqbb *s, double Fc);
+size_t orc_rbb_process(orc_iqbb *s, const int16_t *in, size_t n, int16_t *out_iq);
+
 /* AutoCast< std::complex<int16_t> > from complex 8-bit input (src/autocast.hh:187-204): n BYTES in,
  * n int16 out.  cu8: the bytes are read through an int8_t pointer (reference quirk), (v-127)<<8;
  * cs8: v<<8. */

@@ -79,6 +79,37 @@ def main():
                 am=np.fromfile(pre + ".am", dtype=dt),
                 usb=np.fromfile(pre + ".usb", dtype=dt))
             print("wrote", name, "ss=%d inc=%d outputs=%d" % (hdr[1], hdr[2], np.fromfile(pre + ".counts", dtype=np.uint32).sum()))
+        # real-input BaseBand<int16_t>: name, Fs, Fc, Ff, width, order, ss, buffer_size, N
+        for (name, Fs, Fc, Ff, width, order, ss, bs, N) in [
+                ("rbb_pos", 48000.0, 10e3, 10e3, 3e3, 21, 6, 1000, 9000),
+                ("rbb_neg_even", 2.4e6, -300.5e3, -280e3, 50e3, 32, 50, 4096, 30000),
+                ("rbb_inc0_ss1", 8000.0, 0.0, 1e3, 500.0, 9, 1, 512, 3000)]:
+            t = np.arange(N) / Fs
+            x = (9000 * np.cos(2 * np.pi * abs(Fc if Fc else 1e3) * 1.01 * t) + 4000 * np.cos(2 * np.pi * 0.37 * Fs / 2 * t + 1)).astype(np.int16)
+            x += np.random.Generator(np.random.MT19937(0x5D12000B)).integers(-200, 201, size=N).astype(np.int16)
+            inp = os.path.join(td, name + ".in"); x.tofile(inp)
+            pre = os.path.join(td, name)
+            run(["rbb", inp, bs, repr(Fs), repr(Fc), repr(Ff), repr(width), order, ss, pre])
+            raw = np.fromfile(pre + ".params", dtype=np.uint8)
+            hdr = raw[:32].view(np.int64); L = int(hdr[0])
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), Fs=Fs, Fc=Fc, Ff=Ff, width=width, order=order, sub_sample=ss,
+                                buffer_size=bs, x=x, ref_lut_inc=int(hdr[2]), ref_neg=int(hdr[3]),
+                                ref_kernel=raw[32:32 + 8 * L].view(np.int32).reshape(L, 2),
+                                bb=np.fromfile(pre + ".bb", dtype=np.int16).reshape(-1, 2),
+                                counts=np.fromfile(pre + ".counts", dtype=np.uint32))
+            print("wrote", name, "inc=%d" % hdr[2])
+        # WavSink<T> -> file -> WavSource: the file bytes the reference writes and the buffers it reads back
+        gw = np.random.Generator(np.random.MT19937(0x5D12000C))
+        for typ, dt, ncomp, Fs, bs, frames in (("u8", np.uint8, 1, 8000.0, 512, 1300), ("s16", np.int16, 1, 48000.0, 1024, 2500),
+                                               ("cu8", np.uint8, 2, 1e6, 1024, 3000), ("cs16", np.int16, 2, 2.4e6, 2048, 4096)):
+            x = gw.integers(np.iinfo(dt).min, np.iinfo(dt).max + 1, size=frames * ncomp).astype(dt)
+            inp = os.path.join(td, "wav_" + typ + ".in"); x.tofile(inp)
+            pre = os.path.join(td, "wav_" + typ); wav = pre + ".wav"
+            run(["wav", typ, inp, bs, repr(Fs), wav, pre])
+            np.savez_compressed(os.path.join(HERE, "wav_" + typ + ".npz"), x=x, Fs=Fs, buffer_size=bs,
+                                wav=np.fromfile(wav, dtype=np.uint8), data=np.fromfile(pre + ".data", dtype=np.uint8),
+                                byte_counts=np.fromfile(pre + ".counts", dtype=np.uint32), cfg=np.fromfile(pre + ".cfg"))
+            print("wrote wav_" + typ)
         # AutoCast<complex<int16>> from cu8 / cs8, and FMDeemph<int16> (the nodes either side of the path)
         g = np.random.Generator(np.random.MT19937(0x5D12000A))
         for fmt, dt in (("cu8", np.uint8), ("cs8", np.int8)):

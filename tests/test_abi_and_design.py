@@ -57,6 +57,23 @@ def test_host_design_matches_reference(name):
     assert out.type == {"s16": _lib.T_CS16, "s8": _lib.T_CS8}[str(g["scalar"])]
 
 
+@pytest.mark.parametrize("name", golden_names("rbb_"))
+def test_real_baseband_host_design_matches_reference(name):
+    from libsdr_b200.nodes import BaseBand
+    g = load_golden(name)
+    bb = BaseBand(float(g["Fc"]), float(g["Ff"]), float(g["width"]), int(g["order"]), int(g["sub_sample"]))
+    out = bb.design_only(sample_rate=float(g["Fs"]), buffer_size=int(g["buffer_size"]))
+    inf = bb.info()
+    assert inf.lut_inc == int(g["ref_lut_inc"]) and inf.negative_shift == int(g["ref_neg"])
+    np.testing.assert_array_equal(bb.design()[0], g["ref_kernel"])
+    bs, ss = int(g["buffer_size"]), int(g["sub_sample"])
+    assert out.buffer_size == bs // ss + (1 if bs % ss else 0)
+    assert out.sample_rate == float(g["Fs"]) / ss                 # a double here (baseband.hh:396-397)
+    assert out.type == _lib.T_CS16
+    with pytest.raises(ConfigError):                              # complex input is a type error (baseband.hh:363-369)
+        bb.design_only(Config(_lib.T_CS16, 48e3, 1024, 1))
+
+
 def test_config_error_on_type_mismatch_and_silent_on_incomplete():
     bb = IQBaseBand("s16", 100e3, 100e3, 12.5e3, 15, 1, 48000.0)
     with pytest.raises(ConfigError):

@@ -38,6 +38,25 @@ def test_compat_headers_compile_reference_style_source(tmp_path):
                     "-I" + os.path.join(ROOT, "include"), str(src)], check=True, capture_output=True, text=True)
 
 
+@pytest.mark.parametrize("typ", ["u8", "s16", "cu8", "cs16"])
+def test_wav_sink_and_source_match_reference_files(typ, tmp_path):
+    """WavSink writes the reference's bytes; WavSource reads a reference-written file into the same buffers."""
+    import numpy as np
+    from conftest import load_golden
+    g = load_golden("wav_" + typ)
+    exe = compile_cpp("wav_test")
+    inp, ref, pre = tmp_path / "in.raw", tmp_path / "ref.wav", tmp_path / "out"
+    g["x"].tofile(inp); g["wav"].tofile(ref)
+    r = subprocess.run([exe, typ, str(inp), str(int(g["buffer_size"])), repr(float(g["Fs"])), str(ref), str(pre)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "wav_test: ok" in r.stdout
+    np.testing.assert_array_equal(np.fromfile(str(pre) + ".wav", dtype=np.uint8), g["wav"])
+    np.testing.assert_array_equal(np.fromfile(str(pre) + ".data", dtype=np.uint8), g["data"])
+    np.testing.assert_array_equal(np.fromfile(str(pre) + ".counts", dtype=np.uint32), g["byte_counts"])
+    np.testing.assert_array_equal(np.fromfile(str(pre) + ".cfg"), g["cfg"])
+
+
 @pytest.mark.gpu
 def test_sdr_fm_shaped_chain_bit_exact():
     os.makedirs(BUILD, exist_ok=True)
@@ -69,3 +88,14 @@ def test_full_sdr_fm_chain_with_reference_header_names():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "sdr_fm_test: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_wav_to_wav_real_baseband_fm_chain(tmp_path):
+    os.makedirs(BUILD, exist_ok=True)
+    obj = os.path.join(BUILD, "sdr_oracle.o")
+    subprocess.run(["gcc", "-O2", "-fwrapv", "-c", os.path.join(ROOT, "oracle", "sdr_oracle.c"), "-o", obj], check=True)
+    exe = compile_cpp("wav_chain_test", extra=[obj], compat=True)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "wav_chain_test: ok" in r.stdout

@@ -125,3 +125,16 @@ def test_fmdeemph_matches_reference(name):
     bs = int(g["buffer_size"])
     out = np.concatenate([d.process(g["x"][o:o + bs]) for o in range(0, g["x"].shape[0], bs)])
     np.testing.assert_array_equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names("rbb_"))
+def test_real_baseband_matches_reference(name):
+    g = load_golden(name)
+    o = orc.BaseBand(float(g["Fc"]), float(g["Ff"]), float(g["width"]), int(g["order"]), int(g["sub_sample"]))
+    o.config(float(g["Fs"]), int(g["buffer_size"]))
+    assert o.lut_inc == int(g["ref_lut_inc"])
+    np.testing.assert_array_equal(o.kernel_i32(), g["ref_kernel"])
+    bs = int(g["buffer_size"])
+    outs = [o.process(g["x"][k:k + bs]) for k in range(0, g["x"].shape[0], bs)]
+    np.testing.assert_array_equal(np.array([y.shape[0] for y in outs], dtype=np.uint32), g["counts"])
+    np.testing.assert_array_equal(np.concatenate(outs), g["bb"])
