@@ -105,6 +105,19 @@ __device__ __forceinline__ bool chunk_of(const IqbbFoldArgs &a, uint32_t id, int
   return true;
 }
 
+// Ragged batch of a complete window: RS steps, only the last one predicated (per-lane constant).
+template <int RS>
+__device__ __forceinline__ void ragged_batch(float2 (&R)[8], const float2 *__restrict__ xk, uint32_t ph, uint32_t inc32,
+                                             const float2 *sA, bool last_ok) {
+  float2 xv[RS];
+#pragma unroll
+  for (int u = 0; u + 1 < RS; ++u) xv[u] = ld_stream(xk + 32 * u);
+  xv[RS - 1] = make_float2(0.f, 0.f);
+  if (last_ok) xv[RS - 1] = ld_stream(xk + 32 * (RS - 1));
+#pragma unroll
+  for (int u = 0; u < RS; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
+}
+
 // Persistent grid (one CTA per resident slot); chunk ids are dealt round-robin to the warps of the
 // whole grid, so that at any moment the running warps read ONE compact, linearly advancing region
 // of the input (DRAM row locality, like a grid-stride loop) instead of thousands of separate fronts.
@@ -130,7 +143,60 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
   const int win_off = (int)a.first - (int)a.r0;   // begin(s) = s*ss + win_off (s>0), end(s) = (s+1)*ss + win_off
   const uint32_t inc32 = (32u * a.inc) & 0x7fffu, inc256 = (256u * a.inc) & 0x7fffu;
 
+  // per-lane constants of the interior-window schedule
+  const bool fast_last_ok = (uint32_t)lane < a.fast_pl;
+  const bool fast_t0 = lane < L1, fast_t1 = lane + 32 < L1;
+  const int fast_tlo = (int)a.ss - L1;
+
   for (uint32_t id = wg; id < a.n_chunks; id += total_warps) {
+    // Complete interior window (the common case): every bound is a launch constant, so the chunk
+    // arithmetic, the ragged-batch predicates and the tail addressing of the general path below fold
+    // into a handful of instructions -- the kernel is issue-limited, not byte-limited, beyond ~85 %
+    // of HBM (profiles/r02_fold_probe.md).
+    if (a.fast && id > 0 && (int)((id + 1) * a.ss) + win_off <= (int)a.n) {
+      const int c_lo = (int)(id * a.ss) + win_off;
+      const float2 *__restrict__ xc = x + c_lo + lane;
+      uint32_t ph = (a.phase0 + (uint32_t)(c_lo + lane) * a.inc) & 0x7fffu;
+      const uint32_t r0 = ph & 255u;
+      float2 R[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
+      const float2 *__restrict__ xk = xc;
+      for (uint32_t b = 0; b < a.fast_nb; ++b, xk += 256, ph = (ph + inc256) & 0x7fffu) {
+        float2 xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = ld_stream(xk + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
+      }
+      // tails owed to the next window: loads issued together with the ragged batch
+      const uint32_t pb = (a.phase0 + (uint32_t)(c_lo + (int)a.ss) * a.inc) & 0x7fffu;
+      const float2 Ab = sA[pb >> 8];
+      const float2 *__restrict__ ue = a.tab_u + (size_t)(pb & 255u) * a.taps_len + (L1 - lane);   // U(r_b, e), e = L1 - lane
+      float2 xt0 = make_float2(0.f, 0.f), xt1 = xt0, ut0 = xt0, ut1 = xt0;
+      if (fast_t0) { xt0 = __ldg(xc + fast_tlo); ut0 = __ldg(ue); }
+      if (fast_t1) { xt1 = __ldg(xc + fast_tlo + 32); ut1 = __ldg(ue - 32); }
+      switch (a.fast_rs) {
+        case 1: ragged_batch<1>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        case 2: ragged_batch<2>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        case 3: ragged_batch<3>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        case 4: ragged_batch<4>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        case 5: ragged_batch<5>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        case 6: ragged_batch<6>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        case 7: ragged_batch<7>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        case 8: ragged_batch<8>(R, xk, ph, inc32, sA, fast_last_ok); break;
+        default: break;
+      }
+      float2 sent = make_float2(0.f, 0.f);
+      cfma(sent, cmul(Ab, ut0), xt0);     // zero when this lane has no such sample
+      cfma(sent, cmul(Ab, ut1), xt1);
+      float2 tot = make_float2(-sent.x, -sent.y);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);
+      stage.push(tot, id, lane, acc_out);
+      if (L1 > 0) stage.push(sent, id + 1, lane, acc_out);
+      continue;
+    }
     Chunk c;
     if (lane == 0 && a.pf_dist && id + a.pf_dist * total_warps < a.n_chunks) {   // a later chunk of this warp -> L2, one instruction
       Chunk nx;
@@ -352,6 +418,125 @@ __global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_tma_kernel(cons
   flush(acc_out, base_slot, base, lane);
 }
 
+
+// ---- bandwidth probes (SDRG_FOLD_PROBE=1..3; results are NOT the IQBaseBand output) ---------------
+// Same persistent grid, chunk dealing and staging as iqbb_fold_f32_kernel with the arithmetic reduced
+// to one complex add per sample: what the access pattern itself can reach.  MODE 1: batches of 8 steps
+// (the production schedule); 2: the whole window (<= 16 steps) in one round trip; 3: the first batch of
+// the NEXT chunk is issued before the current chunk's last batch is consumed.
+template <int MODE>
+__global__ void __launch_bounds__(kFoldThreads, MODE == 1 ? 4 : 3) iqbb_fold_probe_kernel(const IqbbFoldArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t total_warps = gridDim.x * kFoldWarps;
+  const uint32_t wg = warp * gridDim.x + blockIdx.x;
+  const float2 *__restrict__ x = (const float2 *)a.x;
+  float *acc_out = (float *)a.acc_cur;
+  WarpStage stage{(float2 *)dyn_smem + (size_t)warp * kStageRows * kStagePitch, 0u, 0u};
+  const int L1 = (int)a.taps_len - 1;
+  const int win_off = (int)a.first - (int)a.r0;
+  if (MODE == 1) {
+    for (uint32_t id = wg; id < a.n_chunks; id += total_warps) {
+      Chunk c;
+      if (!chunk_of(a, id, win_off, L1, c)) continue;
+      const float2 *__restrict__ xc = x + c.c_lo + lane;
+      float2 R[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
+      int k = 0;
+      for (; k + 256 <= c.len; k += 256) {
+        float2 xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = ld_stream(xc + k + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { R[u].x += xv[u].x; R[u].y += xv[u].y; }
+      }
+      if (k < c.len) {
+        const int rem = c.len - k;
+        float2 xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xv[u] = make_float2(0.f, 0.f); if (32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { R[u].x += xv[u].x; R[u].y += xv[u].y; }
+      }
+      float2 tot = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { tot.x += R[u].x; tot.y += R[u].y; }
+      stage.push(tot, c.s, lane, acc_out);
+    }
+  } else if (MODE == 2) {
+    for (uint32_t id = wg; id < a.n_chunks; id += total_warps) {
+      Chunk c;
+      if (!chunk_of(a, id, win_off, L1, c)) continue;
+      const float2 *__restrict__ xc = x + c.c_lo + lane;
+      float2 tot = make_float2(0.f, 0.f);
+      for (int k = 0; k < c.len; k += 512) {
+        const int rem = c.len - k;
+        float2 xv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { xv[u] = make_float2(0.f, 0.f); if (32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u); }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { tot.x += xv[u].x; tot.y += xv[u].y; }
+      }
+      stage.push(tot, c.s, lane, acc_out);
+    }
+  } else {
+    uint32_t id = wg;
+    Chunk c; bool have = false;
+    for (; id < a.n_chunks; id += total_warps) if (chunk_of(a, id, win_off, L1, c)) { have = true; break; }
+    float2 xa[8];
+    if (have) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { xa[u] = make_float2(0.f, 0.f); if (32 * u + lane < c.len) xa[u] = ld_stream(x + c.c_lo + lane + 32 * u); }
+    }
+    while (have) {
+      const float2 *__restrict__ xc = x + c.c_lo + lane;
+      float2 xb[8];
+      const int rem = c.len - 256;                         // second batch of this chunk (issued first)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { xb[u] = make_float2(0.f, 0.f); if (32 * u + lane < rem) xb[u] = ld_stream(xc + 256 + 32 * u); }
+      float2 tot = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { tot.x += xa[u].x; tot.y += xa[u].y; }
+      Chunk cn; bool haven = false;
+      for (id += total_warps; id < a.n_chunks; id += total_warps) if (chunk_of(a, id, win_off, L1, cn)) { haven = true; break; }
+      if (haven) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xa[u] = make_float2(0.f, 0.f); if (32 * u + lane < cn.len) xa[u] = ld_stream(x + cn.c_lo + lane + 32 * u); }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { tot.x += xb[u].x; tot.y += xb[u].y; }
+      for (int k = 512; k < c.len; k += 256) {             // longer pieces: plain batches
+        const int r2 = c.len - k;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xb[u] = make_float2(0.f, 0.f); if (32 * u + lane < r2) xb[u] = ld_stream(xc + k + 32 * u); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { tot.x += xb[u].x; tot.y += xb[u].y; }
+      }
+      stage.push(tot, c.s, lane, acc_out);
+      c = cn; have = haven;
+    }
+  }
+  stage.drain(lane, acc_out);
+}
+
+template <int MODE>
+static int launch_fold_probe(IqbbFoldArgs a, cudaStream_t st) {
+  const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
+  int sms = 0, per_sm = 0;
+  const int dev = current_device();
+  SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_probe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_probe_kernel<MODE>, kFoldThreads, smem));
+  static const int cap = [] { const char *e = getenv("SDRG_FOLD_PROBE_CTAS"); return e ? atoi(e) : 0; }();
+  if (cap > 0 && cap < per_sm) per_sm = cap;
+  const uint64_t resident = (uint64_t)sms * (per_sm > 0 ? per_sm : 1);
+  const uint64_t want = ((uint64_t)a.n_chunks + kFoldWarps - 1) / kFoldWarps;
+  iqbb_fold_probe_kernel<MODE><<<(unsigned)(want < resident ? want : resident), kFoldThreads, smem, st>>>(a);
+  SDRG_CHECK_LAUNCH("iqbb_fold_probe_kernel");
+  return SDRG_OK;
+}
+
 }  // namespace
 
 // Grids are sized to the machine: 148 SMs x 3 resident CTAs of 8 warps.
@@ -367,6 +552,15 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   a.chunks_per_warp = 0;
   static const int pf = [] { const char *e = getenv("SDRG_FOLD_PF"); return e ? atoi(e) : 0; }();   // measured: no gain with round-robin chunks
   a.pf_dist = (uint32_t)pf;
+  static const int fast_env = [] { const char *e = getenv("SDRG_FOLD_FAST"); return e ? atoi(e) : 1; }();
+  a.fast = (fast_env && a.cpw == 1 && a.taps_len <= 65 && a.ss + 1 >= a.taps_len) ? 1u : 0u;
+  a.fast_nb = a.ss / 256;
+  a.fast_rs = (a.ss % 256 + 31) / 32;
+  a.fast_pl = a.ss % 32 ? a.ss % 32 : 32;
+  static const int probe = [] { const char *e = getenv("SDRG_FOLD_PROBE"); return e ? atoi(e) : 0; }();
+  if (probe == 1) return launch_fold_probe<1>(a, st);
+  if (probe == 2) return launch_fold_probe<2>(a, st);
+  if (probe == 3) return launch_fold_probe<3>(a, st);
   static int resident_dev[kMaxDevices] = {0};     // CTAs that fit the device at once: SMs x occupancy
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
   const int dev = current_device();
