@@ -105,6 +105,77 @@ __device__ __forceinline__ bool chunk_of(const IqbbFoldArgs &a, uint32_t id, int
   return true;
 }
 
+// One chunk on the general path: any clipping, any piece of a long window, any tap count.
+__device__ __forceinline__ void fold_chunk_general(const IqbbFoldArgs &a, const uint32_t id, const uint32_t total_warps,
+                                                   const float2 *__restrict__ x, const float2 *sA, const float2 *sH,
+                                                   const int lane, const int L1, const int win_off,
+                                                   const uint32_t inc32, const uint32_t inc256,
+                                                   WarpStage &stage, float *acc_out) {
+    Chunk c;
+    if (lane == 0 && a.pf_dist && id + a.pf_dist * total_warps < a.n_chunks) {   // a later chunk of this warp -> L2, one instruction
+      Chunk nx;
+      if (chunk_of(a, id + a.pf_dist * total_warps, win_off, L1, nx)) prefetch_l2(x + nx.c_lo, x + nx.c_lo + nx.len);
+    }
+    if (!chunk_of(a, id, win_off, L1, c)) return;
+    const int len = c.len;
+    uint32_t ph = (a.phase0 + (uint32_t)(c.c_lo + lane) * a.inc) & 0x7fffu;         // this lane's phase in step 0
+    const uint32_t r0 = ph & 255u;        // low phase byte in step 0; step u has (r0 + u*inc32) & 255 in every batch
+    float2 R[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
+    const float2 *__restrict__ xc = x + c.c_lo + lane;
+
+    // every sample: R_u += A(a_p) x[p]   (its full weight G = H_u A)
+    int k = 0;
+    for (; k + 256 <= len; k += 256, ph = (ph + inc256) & 0x7fffu) {
+      float2 xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xv[u] = ld_stream(xc + k + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
+    }
+    // The last L-1 samples of the window also owe T_e x to the next window.  Their loads (a re-read
+    // of x, L2 resident, and the U(r_b, e) row) are issued together with the ragged batch so that
+    // the window costs two memory round trips, not three.
+    float2 sent = make_float2(0.f, 0.f);
+    const bool has_tail = c.t_lo < len;
+    const int jt = c.t_lo + lane;                                   // this lane's first tail sample
+    float2 Ab = make_float2(0.f, 0.f), xt0 = Ab, xt1 = Ab, ut0 = Ab, ut1 = Ab;
+    const float2 *__restrict__ ue = a.tab_u;
+    if (has_tail) {
+      const uint32_t pb = (a.phase0 + (uint32_t)c.full_end * a.inc) & 0x7fffu;
+      Ab = sA[pb >> 8];
+      ue = a.tab_u + (size_t)(pb & 255u) * a.taps_len + (c.full_end - c.c_lo - lane);   // U(r_b, e), e = end - j
+      if (jt < len) { xt0 = __ldg(xc + (jt - lane)); ut0 = __ldg(ue - (jt - lane)); }
+      if (jt + 32 < len) { xt1 = __ldg(xc + (jt + 32 - lane)); ut1 = __ldg(ue - (jt + 32 - lane)); }
+    }
+    if (k < len) {                        // ragged last batch
+      const int rem = len - k;
+      float2 xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        xv[u] = make_float2(0.f, 0.f);
+        if (32 * u < rem && 32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (32 * u >= rem) break;
+        cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
+      }
+    }
+    if (has_tail) {
+      cfma(sent, cmul(Ab, ut0), xt0);     // zero when this lane has no such sample
+      cfma(sent, cmul(Ab, ut1), xt1);
+      for (int j = jt + 64; j < len; j += 32)       // L > 65 only
+        cfma(sent, cmul(Ab, __ldg(ue - (j - lane))), __ldg(xc + (j - lane)));
+    }
+    float2 tot = make_float2(-sent.x, -sent.y);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);   // H_u = U(r_u, 0)
+    stage.push(tot, c.s, lane, acc_out);
+    if (c.t_lo < len) stage.push(sent, c.s + 1, lane, acc_out);
+}
+
 // Ragged batch of a complete window: RS steps, only the last one predicated (per-lane constant).
 template <int RS>
 __device__ __forceinline__ void ragged_batch(float2 (&R)[8], const float2 *__restrict__ xk, uint32_t ph, uint32_t inc32,
@@ -197,69 +268,7 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
       if (L1 > 0) stage.push(sent, id + 1, lane, acc_out);
       continue;
     }
-    Chunk c;
-    if (lane == 0 && a.pf_dist && id + a.pf_dist * total_warps < a.n_chunks) {   // a later chunk of this warp -> L2, one instruction
-      Chunk nx;
-      if (chunk_of(a, id + a.pf_dist * total_warps, win_off, L1, nx)) prefetch_l2(x + nx.c_lo, x + nx.c_lo + nx.len);
-    }
-    if (!chunk_of(a, id, win_off, L1, c)) continue;
-    const int len = c.len;
-    uint32_t ph = (a.phase0 + (uint32_t)(c.c_lo + lane) * a.inc) & 0x7fffu;         // this lane's phase in step 0
-    const uint32_t r0 = ph & 255u;        // low phase byte in step 0; step u has (r0 + u*inc32) & 255 in every batch
-    float2 R[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
-    const float2 *__restrict__ xc = x + c.c_lo + lane;
-
-    // every sample: R_u += A(a_p) x[p]   (its full weight G = H_u A)
-    int k = 0;
-    for (; k + 256 <= len; k += 256, ph = (ph + inc256) & 0x7fffu) {
-      float2 xv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) xv[u] = ld_stream(xc + k + 32 * u);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
-    }
-    // The last L-1 samples of the window also owe T_e x to the next window.  Their loads (a re-read
-    // of x, L2 resident, and the U(r_b, e) row) are issued together with the ragged batch so that
-    // the window costs two memory round trips, not three.
-    float2 sent = make_float2(0.f, 0.f);
-    const bool has_tail = c.t_lo < len;
-    const int jt = c.t_lo + lane;                                   // this lane's first tail sample
-    float2 Ab = make_float2(0.f, 0.f), xt0 = Ab, xt1 = Ab, ut0 = Ab, ut1 = Ab;
-    const float2 *__restrict__ ue = a.tab_u;
-    if (has_tail) {
-      const uint32_t pb = (a.phase0 + (uint32_t)c.full_end * a.inc) & 0x7fffu;
-      Ab = sA[pb >> 8];
-      ue = a.tab_u + (size_t)(pb & 255u) * a.taps_len + (c.full_end - c.c_lo - lane);   // U(r_b, e), e = end - j
-      if (jt < len) { xt0 = __ldg(xc + (jt - lane)); ut0 = __ldg(ue - (jt - lane)); }
-      if (jt + 32 < len) { xt1 = __ldg(xc + (jt + 32 - lane)); ut1 = __ldg(ue - (jt + 32 - lane)); }
-    }
-    if (k < len) {                        // ragged last batch
-      const int rem = len - k;
-      float2 xv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        xv[u] = make_float2(0.f, 0.f);
-        if (32 * u < rem && 32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (32 * u >= rem) break;
-        cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
-      }
-    }
-    if (has_tail) {
-      cfma(sent, cmul(Ab, ut0), xt0);     // zero when this lane has no such sample
-      cfma(sent, cmul(Ab, ut1), xt1);
-      for (int j = jt + 64; j < len; j += 32)       // L > 65 only
-        cfma(sent, cmul(Ab, __ldg(ue - (j - lane))), __ldg(xc + (j - lane)));
-    }
-    float2 tot = make_float2(-sent.x, -sent.y);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);   // H_u = U(r_u, 0)
-    stage.push(tot, c.s, lane, acc_out);
-    if (c.t_lo < len) stage.push(sent, c.s + 1, lane, acc_out);
+    fold_chunk_general(a, id, total_warps, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out);
   }
   stage.drain(lane, acc_out);
 
@@ -419,6 +428,140 @@ __global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_tma_kernel(cons
 }
 
 
+// ---- window-pipelined variant (ss <= 512, taps <= 65) ---------------------------------------------
+// A complete interior window is S = ceil(ss/32) steps, fully unrolled.  The warp keeps the S loads of
+// its NEXT window in flight while it works on the current one: step i consumes ring[i] and at once
+// re-issues ring[i] for step i of the next window, so the number of outstanding loads per warp is
+// constant (S x 256 B) and a window costs no exposed memory round trip -- the two per window of the
+// batched schedule above were what kept it at ~92 % of HBM.  Edge chunks (window 0, the clipped
+// last window) go through fold_chunk_general.
+template <int S, int P = 0>     // P != 0: timing experiments only (bit 0 no tails, bit 1 no A lookup, bit 2 no H weighting)
+__global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) iqbb_fold_f32_win_kernel(const IqbbFoldArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ float2 sA[128];
+  __shared__ float2 sH[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t k = blockIdx.x * blockDim.x + tid; k < a.zero_next; k += gridDim.x * blockDim.x)
+    ((float2 *)a.acc_next)[k] = make_float2(0.f, 0.f);
+  if (tid < 128) sA[tid] = a.tab_a[tid];
+  sH[tid] = a.tab_u[(size_t)tid * a.taps_len];
+  __syncthreads();
+
+  const uint32_t T = gridDim.x * kFoldWarps;
+  const uint32_t wg = warp * gridDim.x + blockIdx.x;
+  const float2 *__restrict__ x = (const float2 *)a.x;
+  float *acc_out = (float *)a.acc_cur;
+  WarpStage stage{(float2 *)dyn_smem + (size_t)warp * kStageRows * kStagePitch, 0u, 0u};
+  const int L1 = (int)a.taps_len - 1;
+  const int win_off = (int)a.first - (int)a.r0;
+  const uint32_t inc32 = (32u * a.inc) & 0x7fffu, inc256 = (256u * a.inc) & 0x7fffu;
+  const bool last_ok = (uint32_t)lane < a.fast_pl;
+  int te[3]; bool te_ok[3];                   // tail distance of this lane's sample in ring step S-1-k
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { te[k] = (int)a.ss - 32 * (S - 1 - k) - lane; te_ok[k] = te[k] >= 1 && te[k] <= L1; }
+
+  uint32_t id = wg;
+  if (id == 0) { fold_chunk_general(a, 0u, T, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out); id += T; }
+  if (id <= a.fast_hi) {
+    const float2 *__restrict__ xc = x + ((int)(id * a.ss) + win_off) + lane;
+    const size_t stride = (size_t)T * a.ss;                      // this warp's next window
+    uint32_t ph = a.phase0 + (uint32_t)((int)(id * a.ss) + win_off + lane) * a.inc;   // only bits 0..14 are used
+    uint32_t pb = a.phase0 + (uint32_t)((int)((id + 1) * a.ss) + win_off) * a.inc;
+    const uint32_t dph = (uint32_t)stride * a.inc;
+    float2 ring[S];
+#pragma unroll
+    for (int i = 0; i + 1 < S; ++i) ring[i] = ld_stream(xc + 32 * i);
+    ring[S - 1] = make_float2(0.f, 0.f);
+    if (last_ok) ring[S - 1] = ld_stream(xc + 32 * (S - 1));
+    for (;;) {
+      const bool more = id + T <= a.fast_hi;
+      const float2 *__restrict__ xn = xc + stride;
+      // Tails owed to the next window: the last L-1 samples of the window sit in the last (up to three)
+      // ring steps already, so only their weights U(r_b, e), e = ss - 32 i - lane, are fetched (issued
+      // now, used ~a window later).  e and its validity are per-lane constants of the launch.
+      const float2 Ab = sA[(pb & 0x7fffu) >> 8];
+      const float2 *__restrict__ urow = a.tab_u + (size_t)(pb & 255u) * a.taps_len;
+      float2 ut[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        ut[k] = make_float2(0.f, 0.f);
+        if (!(P & 1) && k < S && te_ok[k]) ut[k] = (P & 8) ? Ab : __ldg(urow + te[k]);
+      }
+      float2 R[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
+      float2 ts = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        if (P & 2) cfma(R[i & 7], Ab, ring[i]);
+        else cfma(R[i & 7], sA[((ph + i * inc32) & 0x7fffu) >> 8], ring[i]);
+        if (!(P & 1) && S - 1 - i < 3) cfma(ts, ut[S - 1 - i], ring[i]);     // zero weight outside the tail
+        if (more) {
+          if (i + 1 < S) ring[i] = ld_stream(xn + 32 * i);
+          else if (last_ok) ring[i] = ld_stream(xn + 32 * i);    // lanes past the window keep their zero
+        }
+      }
+      const float2 sent = cmul(Ab, ts);
+      float2 tot = make_float2(-sent.x, -sent.y);
+      const uint32_t r0 = ph & 255u;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (P & 4) { tot.x += R[u].x; tot.y += R[u].y; }
+        else cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);
+      }
+      stage.push(tot, id, lane, acc_out);
+      if (L1 > 0 && !(P & 1)) stage.push(sent, id + 1, lane, acc_out);
+      id += T;
+      if (!more) break;
+      xc = xn; ph += dph; pb += dph;
+    }
+  }
+  for (; id < a.n_chunks; id += T) fold_chunk_general(a, id, T, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out);
+  stage.drain(lane, acc_out);
+}
+
+template <int S, int P = 0>
+static int launch_fold_win_s(const IqbbFoldArgs &a, cudaStream_t st) {
+  static int resident_dev[kMaxDevices] = {0};
+  const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
+  const int dev = current_device();
+  if (!resident_dev[dev]) {
+    SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_win_kernel<S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, per_sm = 0;
+    SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_f32_win_kernel<S, P>, kFoldThreads, smem));
+    resident_dev[dev] = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const uint64_t resident = (uint64_t)resident_dev[dev];
+  const uint64_t want = ((uint64_t)a.n_chunks + kFoldWarps - 1) / kFoldWarps;
+  iqbb_fold_f32_win_kernel<S, P><<<(unsigned)(want < resident ? want : resident), kFoldThreads, smem, st>>>(a);
+  SDRG_CHECK_LAUNCH("iqbb_fold_f32_win_kernel");
+  return SDRG_OK;
+}
+
+static int launch_fold_win(const IqbbFoldArgs &a, cudaStream_t st) {
+  static const int wp = [] { const char *e = getenv("SDRG_FOLD_WINP"); return e ? atoi(e) : 0; }();   // experiments, S = 13 only
+  if (wp && (a.ss + 31) / 32 == 13) {
+    switch (wp) {
+      case 1: return launch_fold_win_s<13, 1>(a, st); case 2: return launch_fold_win_s<13, 2>(a, st);
+      case 3: return launch_fold_win_s<13, 3>(a, st); case 4: return launch_fold_win_s<13, 4>(a, st);
+      case 5: return launch_fold_win_s<13, 5>(a, st); case 6: return launch_fold_win_s<13, 6>(a, st);
+      case 7: return launch_fold_win_s<13, 7>(a, st); case 8: return launch_fold_win_s<13, 8>(a, st); default: break;
+    }
+  }
+  switch ((a.ss + 31) / 32) {
+    case 1: return launch_fold_win_s<1>(a, st);   case 2: return launch_fold_win_s<2>(a, st);
+    case 3: return launch_fold_win_s<3>(a, st);   case 4: return launch_fold_win_s<4>(a, st);
+    case 5: return launch_fold_win_s<5>(a, st);   case 6: return launch_fold_win_s<6>(a, st);
+    case 7: return launch_fold_win_s<7>(a, st);   case 8: return launch_fold_win_s<8>(a, st);
+    case 9: return launch_fold_win_s<9>(a, st);   case 10: return launch_fold_win_s<10>(a, st);
+    case 11: return launch_fold_win_s<11>(a, st); case 12: return launch_fold_win_s<12>(a, st);
+    case 13: return launch_fold_win_s<13>(a, st); case 14: return launch_fold_win_s<14>(a, st);
+    case 15: return launch_fold_win_s<15>(a, st); case 16: return launch_fold_win_s<16>(a, st);
+    default: return set_error(SDRG_ERR_RUNTIME, "IQBaseBand<float>: window-pipelined kernel needs sub_sample <= 512");
+  }
+}
+
 // ---- bandwidth probes (SDRG_FOLD_PROBE=1..3; results are NOT the IQBaseBand output) ---------------
 // Same persistent grid, chunk dealing and staging as iqbb_fold_f32_kernel with the arithmetic reduced
 // to one complex add per sample: what the access pattern itself can reach.  MODE 1: batches of 8 steps
@@ -557,7 +700,14 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   a.fast_nb = a.ss / 256;
   a.fast_rs = (a.ss % 256 + 31) / 32;
   a.fast_pl = a.ss % 32 ? a.ss % 32 : 32;
+  a.fast_hi = 0;
+  if (a.fast) {      // ids 1..fast_hi: (id + 1) * ss + first - r0 <= n
+    const int64_t hi = ((int64_t)a.n + (int64_t)a.r0 - (int64_t)a.first) / (int64_t)a.ss - 1;
+    a.fast_hi = hi >= 1 ? (uint32_t)hi : 0u;
+  }
+  static const int win_env = [] { const char *e = getenv("SDRG_FOLD_WIN"); return e ? atoi(e) : 1; }();
   static const int probe = [] { const char *e = getenv("SDRG_FOLD_PROBE"); return e ? atoi(e) : 0; }();
+  if (!probe && win_env && a.fast && a.ss <= 512 && a.fast_hi >= 1) return launch_fold_win(a, st);
   if (probe == 1) return launch_fold_probe<1>(a, st);
   if (probe == 2) return launch_fold_probe<2>(a, st);
   if (probe == 3) return launch_fold_probe<3>(a, st);

@@ -61,6 +61,7 @@ struct IqbbFoldArgs {
   uint32_t      fast_nb;    // full 256-sample batches per window (ss / 256)
   uint32_t      fast_rs;    // 32-sample steps of the ragged batch (0..8)
   uint32_t      fast_pl;    // lanes of its last step (1..32)
+  uint32_t      fast_hi;    // chunk ids 1..fast_hi are complete interior windows (0 = none)
 };
 
 // finalize (+ optional demodulation) of the completed windows of one call
