@@ -275,7 +275,8 @@ def test_float_small_configs(demod, path):
         _float_case(cfg, x, 40000, demod, path)
 
 
-@pytest.mark.parametrize("ss,order", [(32, 33), (63, 64), (64, 64), (100, 2), (416, 1), (417, 64), (5000, 64), (8191, 64), (8192, 64), (8193, 64), (300000, 128)])
+@pytest.mark.parametrize("ss,order", [(32, 33), (33, 2), (63, 64), (64, 64), (100, 2), (416, 1), (417, 64), (512, 65), (513, 65), (600, 40),
+                                      (768, 64), (1000, 64), (2083, 15), (5000, 64), (8191, 64), (8192, 64), (8193, 64), (300000, 128)])
 @pytest.mark.parametrize("path", [2, 3], ids=["folded", "folded-tma"])
 def test_float_folded_geometry(ss, order, path):
     """Folded kernel across window/segment geometries (window << segment, window >> segment,
