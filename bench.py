@@ -16,7 +16,7 @@ Metric: input IQ Msamples/s.
   cpu_baseline : the oracle port (the reference has no float instantiation) on one host core
 
 N > 1: one process per GPU, every rank runs its own independent stream (weak scaling, no data-path
-collective); the demodulated audio of all ranks is gathered with NCCL each step.
+collective); the demodulated audio of all ranks is gathered with NCCL (all_gather batched over 8 steps, overlapped with the next steps).
 """
 import argparse
 import json
@@ -290,6 +290,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's version/info banner goes to stdout too, so it is
+        # silenced unless asked for (SDRG_NCCL_DEBUG=INFO shows the NVLS/ring choice; not a timed run then)
+        os.environ["NCCL_DEBUG"] = os.environ.get("SDRG_NCCL_DEBUG", "WARN")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
