@@ -19,6 +19,7 @@
 // (j div Ns) Ns R + (j mod Ns) + r Ns.  Twiddles come from a table of n-th roots of unity computed
 // in double on the host.  Data ping-pongs between shared-memory buffers; one __syncthreads per stage.
 #include "fft_kernels.cuh"
+#include <cstdlib>
 
 namespace sdrg {
 namespace {
@@ -50,6 +51,35 @@ template <bool INV> __device__ __forceinline__ void dft8(float2 *v) {
   float2 t;
   t = v[1]; v[1] = v[4]; v[4] = t;
   t = v[3]; v[3] = v[6]; v[6] = t;
+}
+
+// 16-point DFT as 4 x 4 (Cooley-Tukey): DFT4 over r1 of v[4 r1 + r0], twiddle w16^(r0 q0), DFT4 over r0;
+// result V[4 q1 + q0] in natural order.
+template <bool INV> __device__ __forceinline__ float2 mulw16(float2 a, const float c, const float sn) {
+  // a * (c - i sn) forward, a * (c + i sn) inverse
+  return INV ? make_float2(a.x * c - a.y * sn, a.y * c + a.x * sn) : make_float2(a.x * c + a.y * sn, a.y * c - a.x * sn);
+}
+template <bool INV> __device__ __forceinline__ void dft16(float2 *v) {
+  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  float2 a[4][4];                                   // a[r0][q0]
+#pragma unroll
+  for (int r0 = 0; r0 < 4; ++r0) {
+    float2 t[4] = {v[r0], v[4 + r0], v[8 + r0], v[12 + r0]};
+    dft4<INV>(t);
+#pragma unroll
+    for (int q0 = 0; q0 < 4; ++q0) a[r0][q0] = t[q0];
+  }
+  // w16^(r0 q0): exponents 1,2,3 / 2,4,6 / 3,6,9
+  a[1][1] = mulw16<INV>(a[1][1], c1, s1); a[1][2] = mulw16<INV>(a[1][2], h, h);  a[1][3] = mulw16<INV>(a[1][3], s1, c1);
+  a[2][1] = mulw16<INV>(a[2][1], h, h);   a[2][2] = rot90<INV>(a[2][2]);         a[2][3] = mulw16<INV>(a[2][3], -h, h);
+  a[3][1] = mulw16<INV>(a[3][1], s1, c1); a[3][2] = mulw16<INV>(a[3][2], -h, h); a[3][3] = mulw16<INV>(a[3][3], -c1, -s1);
+#pragma unroll
+  for (int q0 = 0; q0 < 4; ++q0) {
+    float2 t[4] = {a[0][q0], a[1][q0], a[2][q0], a[3][q0]};
+    dft4<INV>(t);
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) v[4 * q1 + q0] = t[q1];
+  }
 }
 
 // Shared-memory index padding: one spare element after every 16 (= one 128-byte row of 8-byte
@@ -145,19 +175,31 @@ __device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const in
       if (k > 0) {
         float2 w1 = __ldg(tw + k * tstep);
         if (INV) w1.y = -w1.y;
-        v[b][1] = cmulf(v[b][1], w1);
-        if (R > 2) {
-          const float2 w2 = cmulf(w1, w1), w3 = cmulf(w2, w1);
-          v[b][2] = cmulf(v[b][2], w2); v[b][3] = cmulf(v[b][3], w3);
-          if (R > 4) {
-            const float2 w4 = cmulf(w2, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
-            v[b][4] = cmulf(v[b][4], w4); v[b][5] = cmulf(v[b][5], w5); v[b][6] = cmulf(v[b][6], w6); v[b][7] = cmulf(v[b][7], w7);
+        if (R <= 8) {
+          v[b][1] = cmulf(v[b][1], w1);
+          if (R > 2) {
+            const float2 w2 = cmulf(w1, w1), w3 = cmulf(w2, w1);
+            v[b][2] = cmulf(v[b][2], w2); v[b][3] = cmulf(v[b][3], w3);
+            if (R > 4) {
+              const float2 w4 = cmulf(w2, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
+              v[b][4] = cmulf(v[b][4], w4); v[b][5] = cmulf(v[b][5], w5); v[b][6] = cmulf(v[b][6], w6); v[b][7] = cmulf(v[b][7], w7);
+            }
+          }
+        } else {
+          // radix 16: two chains stepping by w^2 (depth 7), only w1, w2 and the two heads stay live
+          const float2 w2 = cmulf(w1, w1);
+          float2 we = w2, wo = w1;
+#pragma unroll
+          for (int r = 1; r < R; r += 2) {
+            v[b][r] = cmulf(v[b][r], wo);
+            if (r + 1 < R) { v[b][r + 1] = cmulf(v[b][r + 1], we); wo = cmulf(wo, w2); we = cmulf(we, w2); }
           }
         }
       }
       if (R == 2) dft2<INV>(v[b][0], v[b][1]);
       else if (R == 4) dft4<INV>(v[b]);
-      else dft8<INV>(v[b]);
+      else if (R == 8) dft8<INV>(v[b]);
+      else dft16<INV>(v[b]);
     }
   }
   __syncthreads();
@@ -185,6 +227,55 @@ __device__ void fft_smem_inplace(float2 *buf, const int n, const int log2n, cons
     else if (left >= 2) { stage_inplace<4, INV, EPT / 4>(buf, n, Ns, tw, m); Ns *= 4; left -= 2; }
     else { stage_inplace<2, INV, EPT / 2>(buf, n, Ns, tw, m); Ns *= 2; left -= 1; }
     first = false;
+  }
+}
+
+// Stages for the middle `bits` bits of a transform whose first (forward) or last (inverse) radix-2
+// stage is fused into the global load / store: radix 16 while possible, then 8 / 4 / 2.
+template <bool INV>
+__device__ void fft_smem_inplace16(float2 *buf, const int n, int Ns, int left, const float2 *tw, const float2 *mul) {
+  bool first = true;
+  while (left > 0) {
+    const float2 *m = first ? mul : nullptr;
+    if (left >= 4 && left != 5) { stage_inplace<16, INV, 1>(buf, n, Ns, tw, m); Ns *= 16; left -= 4; }
+    else if (left >= 3) { stage_inplace<8, INV, 2>(buf, n, Ns, tw, m); Ns *= 8; left -= 3; }
+    else if (left >= 2) { stage_inplace<4, INV, 4>(buf, n, Ns, tw, m); Ns *= 4; left -= 2; }
+    else { stage_inplace<2, INV, 8>(buf, n, Ns, tw, m); Ns *= 2; left -= 1; }
+    first = false;
+  }
+}
+
+// Single-filter overlap-save, radix-16 plan (n = 2N >= 512, 16 elements per thread).  The forward
+// transform's first radix-2 stage has no twiddles (Ns = 1) and is applied while the two input blocks
+// are loaded; the inverse transform's LAST radix-2 stage (Ns = N) is applied while storing, and only
+// its second half -- the N valid overlap-save outputs y[N + j] = a[j] - w^j b[j] -- is evaluated.
+// At n = 8192 that leaves 3 + 3 shared-memory passes (16 x 16 x 16) instead of 5 + 5.
+__global__ void __launch_bounds__(512, 2) filter_ola1_r16_kernel(const FilterArgs a) {
+  extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+  const int N = a.block, n = 2 * N;
+  float2 *s0 = (float2 *)fft_smem_raw;
+  const int b = blockIdx.x;
+  const float2 *x = (const float2 *)a.x;
+  const float2 *prev = b == 0 ? (const float2 *)a.hist_in : x + (size_t)(b - 1) * N;
+  const float2 *cur = x + (size_t)b * N;
+  const bool roll = b == (int)gridDim.x - 1;
+  float2 *ho = (float2 *)a.hist_out;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float2 p = prev[i], c = cur[i];
+    s0[pidx(2 * i)] = caddf(p, c);                 // Stockham radix-2, Ns = 1: dst[2j] = x[j] + x[j + n/2]
+    s0[pidx(2 * i + 1)] = csubf(p, c);
+    if (roll) ho[i] = c;
+  }
+  __syncthreads();
+  const float2 *tw = (const float2 *)a.tw;
+  fft_smem_inplace16<false>(s0, n, 2, a.log2n - 1, tw, nullptr);
+  fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, (const float2 *)a.kern);
+  const float sc = 1.0f / (float)n;
+  float2 *o = (float2 *)a.out + (size_t)b * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    float2 w = __ldg(tw + j); w.y = -w.y;          // exp(+2 pi i j / n)
+    const float2 v = csubf(s0[pidx(j)], cmulf(s0[pidx(N + j)], w));
+    o[j] = make_float2(v.x * sc, v.y * sc);
   }
 }
 
@@ -290,6 +381,17 @@ int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
     if (smem1 > 48 * 1024 && smem1 > attr1[dev]) {
       SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       attr1[dev] = smem1;
+    }
+    static const int r16 = [] { const char *e = getenv("SDRG_FFT_R16"); return e ? atoi(e) : 1; }();
+    if (r16) {
+      static size_t attr16[kMaxDevices] = {0};
+      if (smem1 > 48 * 1024 && smem1 > attr16[dev]) {
+        SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_r16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        attr16[dev] = smem1;
+      }
+      filter_ola1_r16_kernel<<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
+      SDRG_CHECK_LAUNCH("filter_ola1_r16_kernel");
+      return SDRG_OK;
     }
     filter_ola1_kernel<<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
     SDRG_CHECK_LAUNCH("filter_ola1_kernel");
