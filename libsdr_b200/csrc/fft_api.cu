@@ -79,6 +79,7 @@ struct sdrg_filter {
   void *d_hist[2] = {nullptr, nullptr}; int parity = 0;
   void *d_pend = nullptr; size_t pending = 0;          // re-chunking (BufferNode): < block samples waiting
   void *d_stage = nullptr; size_t stage_cap = 0;
+  void *d_spec = nullptr; size_t spec_cap = 0;         // filter banks: block spectra shared by the filters
   cudaStream_t stream = nullptr;
   void *d_in = nullptr, *d_out = nullptr; size_t in_cap = 0, out_cap = 0;
 };
@@ -203,7 +204,7 @@ int sdrg_filter_destroy(sdrg_filter *h) {
   cudaSetDevice(h->device); cudaDeviceSynchronize();
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->d_tw); cudaFree(h->d_kern); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
-  cudaFree(h->d_pend); cudaFree(h->d_stage); cudaFree(h->d_in); cudaFree(h->d_out);
+  cudaFree(h->d_pend); cudaFree(h->d_stage); cudaFree(h->d_spec); cudaFree(h->d_in); cudaFree(h->d_out);
   delete h;
   return SDRG_OK;
 }
@@ -294,6 +295,13 @@ int sdrg_filter_process_dev(sdrg_filter *h, const void *d_in, size_t n_in, void 
     a.x = src; a.hist_in = h->d_hist[h->parity]; a.hist_out = h->d_hist[h->parity ^ 1];
     a.kern = h->d_kern; a.out = d_out; a.out_stride = out_stride; a.tw = h->d_tw;
     a.block = (int)N; a.log2n = h->log2n; a.n_filters = (int)h->bands.size();
+    a.spec = nullptr;
+    const size_t spec_bytes = nblk * 2 * N * sb;
+    if (a.n_filters > 1 && 2 * N >= 512 && spec_bytes <= ((size_t)2 << 30)) {
+      rc = grow_dev(&h->d_spec, &h->spec_cap, spec_bytes);
+      if (rc) return rc;
+      a.spec = h->d_spec;
+    }
     rc = launch_filter_ola(a, nblk, st);
     if (rc) return rc;
     h->parity ^= 1;

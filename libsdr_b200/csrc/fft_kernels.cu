@@ -250,28 +250,47 @@ __device__ void fft_smem_inplace16(float2 *buf, const int n, int Ns, int left, c
 // are loaded; the inverse transform's LAST radix-2 stage (Ns = N) is applied while storing, and only
 // its second half -- the N valid overlap-save outputs y[N + j] = a[j] - w^j b[j] -- is evaluated.
 // At n = 8192 that leaves 3 + 3 shared-memory passes (16 x 16 x 16) instead of 5 + 5.
+// MODE 0: forward + inverse fused (one filter).  MODE 1: forward only, the spectrum of block b goes to
+// a.spec (a filter bank shares it).  MODE 2: inverse only for filter blockIdx.y, reading a.spec.
+template <int MODE>
 __global__ void __launch_bounds__(512, 2) filter_ola1_r16_kernel(const FilterArgs a) {
   extern __shared__ __align__(16) unsigned char fft_smem_raw[];
   const int N = a.block, n = 2 * N;
   float2 *s0 = (float2 *)fft_smem_raw;
   const int b = blockIdx.x;
-  const float2 *x = (const float2 *)a.x;
-  const float2 *prev = b == 0 ? (const float2 *)a.hist_in : x + (size_t)(b - 1) * N;
-  const float2 *cur = x + (size_t)b * N;
-  const bool roll = b == (int)gridDim.x - 1;
-  float2 *ho = (float2 *)a.hist_out;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const float2 p = prev[i], c = cur[i];
-    s0[pidx(2 * i)] = caddf(p, c);                 // Stockham radix-2, Ns = 1: dst[2j] = x[j] + x[j + n/2]
-    s0[pidx(2 * i + 1)] = csubf(p, c);
-    if (roll) ho[i] = c;
-  }
-  __syncthreads();
   const float2 *tw = (const float2 *)a.tw;
-  fft_smem_inplace16<false>(s0, n, 2, a.log2n - 1, tw, nullptr);
-  fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, (const float2 *)a.kern);
+  if (MODE != 2) {
+    const float2 *x = (const float2 *)a.x;
+    const float2 *prev = b == 0 ? (const float2 *)a.hist_in : x + (size_t)(b - 1) * N;
+    const float2 *cur = x + (size_t)b * N;
+    const bool roll = b == (int)gridDim.x - 1;
+    float2 *ho = (float2 *)a.hist_out;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const float2 p = prev[i], c = cur[i];
+      s0[pidx(2 * i)] = caddf(p, c);                 // Stockham radix-2, Ns = 1: dst[2j] = x[j] + x[j + n/2]
+      s0[pidx(2 * i + 1)] = csubf(p, c);
+      if (roll) ho[i] = c;
+    }
+    __syncthreads();
+    fft_smem_inplace16<false>(s0, n, 2, a.log2n - 1, tw, nullptr);
+  }
+  if (MODE == 1) {
+    float2 *X = (float2 *)a.spec + (size_t)b * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) X[i] = s0[pidx(i)];
+    return;
+  }
+  const int f = MODE == 2 ? (int)blockIdx.y : 0;
+  const float2 *K = (const float2 *)a.kern + (size_t)f * n;
+  if (MODE == 2) {
+    const float2 *X = (const float2 *)a.spec + (size_t)b * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s0[pidx(i)] = cmulf(X[i], __ldg(K + i));
+    __syncthreads();
+    fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, nullptr);
+  } else {
+    fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, K);
+  }
   const float sc = 1.0f / (float)n;
-  float2 *o = (float2 *)a.out + (size_t)b * N;
+  float2 *o = (float2 *)a.out + (size_t)f * a.out_stride + (size_t)b * N;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
     float2 w = __ldg(tw + j); w.y = -w.y;          // exp(+2 pi i j / n)
     const float2 v = csubf(s0[pidx(j)], cmulf(s0[pidx(N + j)], w));
@@ -375,26 +394,29 @@ int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
     attr[dev] = smem;
   }
   int threads = n / 8; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
-  if (a.n_filters == 1 && n >= 512) {          // one filter: in-place stages on a single buffer (n == 16 * threads)
+  static const int r16 = [] { const char *e = getenv("SDRG_FFT_R16"); return e ? atoi(e) : 1; }();
+  if (n >= 512 && (a.n_filters == 1 || (r16 && a.spec))) {   // in-place stages on a single buffer (n == 16 * threads)
     const size_t smem1 = (size_t)padded_len(n) * sizeof(float2);
     static size_t attr1[kMaxDevices] = {0};
     if (smem1 > 48 * 1024 && smem1 > attr1[dev]) {
       SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_r16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_r16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_r16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       attr1[dev] = smem1;
     }
-    static const int r16 = [] { const char *e = getenv("SDRG_FFT_R16"); return e ? atoi(e) : 1; }();
-    if (r16) {
-      static size_t attr16[kMaxDevices] = {0};
-      if (smem1 > 48 * 1024 && smem1 > attr16[dev]) {
-        SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_r16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        attr16[dev] = smem1;
-      }
-      filter_ola1_r16_kernel<<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
+    if (!r16) {
+      filter_ola1_kernel<<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
+      SDRG_CHECK_LAUNCH("filter_ola1_kernel");
+    } else if (a.n_filters == 1) {
+      filter_ola1_r16_kernel<0><<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
       SDRG_CHECK_LAUNCH("filter_ola1_r16_kernel");
-      return SDRG_OK;
+    } else {                                    // bank: one forward pass, then every (block, filter) pair on its own CTA
+      filter_ola1_r16_kernel<1><<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
+      SDRG_CHECK_LAUNCH("filter_ola1_r16_kernel<fwd>");
+      filter_ola1_r16_kernel<2><<<dim3((unsigned)n_blocks, (unsigned)a.n_filters), n / 16, smem1, st>>>(a);
+      SDRG_CHECK_LAUNCH("filter_ola1_r16_kernel<inv>");
     }
-    filter_ola1_kernel<<<(unsigned)n_blocks, n / 16, smem1, st>>>(a);
-    SDRG_CHECK_LAUNCH("filter_ola1_kernel");
     return SDRG_OK;
   }
   filter_ola_kernel<<<(unsigned)n_blocks, threads, smem, st>>>(a);

@@ -17,6 +17,7 @@ struct FilterArgs {
   int         block;
   int         log2n;      // log2(2*block)
   int         n_filters;
+  void       *spec;       // multi-filter radix-16 path: spectra of the blocks, n_blocks x 2*block (null: fused 3-buffer kernel)
 };
 
 int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st);
