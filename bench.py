@@ -248,6 +248,29 @@ def secondary_workloads(world, rank, dev, dist, args):
                            "imad_pipe_frac_est": bs * nb / (ms * 1e-3) * (3 * 14 + 4) / (148 * 64 * 1.965e9)}
     except Exception as e:  # pragma: no cover
         out["c1_int16"] = {"error": str(e)[:200]}
+    try:   # SURVEY 8(f) rows next to the path: RTL-style cu8 input with AutoCast fused into the load, and the real-input BaseBand<int16>
+        from libsdr_b200 import _lib as L
+        from libsdr_b200.nodes import BaseBand
+        c = dict(synth.C1)
+        bs, nb = c["buffer_size"], 2048
+        g = torch.Generator(device="cpu"); g.manual_seed(0x5D12)
+        x8 = torch.randint(0, 256, (nb * bs, 2), dtype=torch.uint8, generator=g).to(dev)
+        bb = IQBaseBand("s16", c["Fc"], c["Ff"], c["width"], c["order"], c["sub_sample"], c["oFs"])
+        bb.setInputType(L.T_CU8); bb.config(sample_rate=c["Fs"], buffer_size=bs)
+        ch = RxChain(bb, DEMOD_FM)
+        ms = _time_steps(lambda: ch.process(x8, bs), 5, 2, barrier)
+        out["c1_cu8_fused_autocast"] = {"workload": "complex uint8 -> AutoCast fused into IQBaseBand<int16> (15 taps, ss=50) + FMDemod, %d buffers of %d" % (nb, bs),
+                                        "msamples_per_s": bs * nb / ms / 1e3, "ms_per_step": ms,
+                                        "algorithmic_gbs": (2 + 2 / 50) * bs * nb / ms / 1e6, "bound": "FMA-heavy (IMAD) pipe (bit-exact path)"}
+        xr = torch.randint(-32768, 32768, (nb * bs,), dtype=torch.int16, generator=g).to(dev)
+        rb = BaseBand(300e3, 300e3, 50e3, 32, 50); rb.config(sample_rate=c["Fs"], buffer_size=bs)
+        chr_ = RxChain(rb, DEMOD_FM)
+        ms = _time_steps(lambda: chr_.process(xr, bs), 5, 2, barrier)
+        out["real_baseband_int16"] = {"workload": "BaseBand<int16> on a real int16 stream (32 taps, ss=50) + FMDemod, %d buffers of %d" % (nb, bs),
+                                      "msamples_per_s": bs * nb / ms / 1e3, "ms_per_step": ms,
+                                      "algorithmic_gbs": (2 + 2 / 50) * bs * nb / ms / 1e6, "bound": "FMA-heavy (IMAD) pipe (bit-exact path)"}
+    except Exception as e:  # pragma: no cover
+        out["next_rows"] = {"error": str(e)[:200]}
     try:   # C3: FFT-convolution filter, block 4096
         c = dict(synth.C3)
         nb = c["n_buffers"]

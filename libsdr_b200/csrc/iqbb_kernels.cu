@@ -241,8 +241,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // Persistent CTAs (one per resident slot) walk the tiles grid-stride; the next tile is fetched into
 // the other shared buffer with cp.async (LDGSTS: no registers, no scoreboard stall) while the current
 // one is being filtered, so the global-load latency that used to head every tile is hidden.
-template <int LP, bool IS_S8>
+// VAR: 0 complex int16 (also the fused 8-bit AutoCast formats), 1 complex int8, 2 REAL int16 (BaseBand<int16_t>:
+// the imaginary input is 0, so the Gauss form collapses to two multiplies per tap: re = sum kr x, im = re + sum (ki-kr) x).
+template <int LP, int VAR>
 __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccumArgs a, const __grid_constant__ IqbbTaps taps) {
+  constexpr bool IS_S8 = VAR == 1, REAL = VAR == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int H = LP - 1;
   constexpr int NV = (LP + 7 + 3) / 4;                 // 128-bit loads per thread
@@ -265,6 +268,9 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccu
     if (interior && !IS_S8 && a.in_fmt == 0) {
       const uint32_t *xg = (const uint32_t *)a.x + (tile_base - H);
       for (int k = tid; k < n_xs; k += kT) cp_async4(xs + k, xg + k);
+    } else if (interior && !IS_S8) {                               // 8-bit / real input formats: convert while staging, no bounds
+      const int64_t i0 = tile_base - H;
+      for (int k = tid; k < n_xs; k += kT) xs[k] = load_cs16(a.x, i0 + k, a.in_fmt);
     } else {
       for (int k = tid; k < n_xs; k += kT) {
         const int64_t i = tile_base - H + k;
@@ -313,9 +319,14 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccu
 #pragma unroll
       for (int r = 0; r < kR; ++r) {
         const int s = (r + tt) & (kR - 1);
-        A1[r] += (uint32_t)c.x * (uint32_t)ws[s];
-        A2[r] += (uint32_t)c.y * (uint32_t)wr[s];
-        A3[r] += (uint32_t)c.z * (uint32_t)wi[s];
+        if (REAL) {
+          A1[r] += (uint32_t)c.x * (uint32_t)wr[s];
+          A2[r] += (uint32_t)c.y * (uint32_t)wr[s];
+        } else {
+          A1[r] += (uint32_t)c.x * (uint32_t)ws[s];
+          A2[r] += (uint32_t)c.y * (uint32_t)wr[s];
+          A3[r] += (uint32_t)c.z * (uint32_t)wi[s];
+        }
       }
       if (tt + 1 < LP) {
         unpack16(w[tt + kR], wr[tt & (kR - 1)], wi[tt & (kR - 1)]);
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_fixed_kernel(const IqbbAccu
   }
 }
 
-template <int LP, bool IS_S8>
+template <int LP, int VAR>
 int launch_fixed(const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned n_tiles, cudaStream_t st) {
   constexpr int NV = (LP + 7 + 3) / 4;
   constexpr int xs_pitch = (kTile + 4 * NV + 8 + 3) & ~3;
@@ -357,19 +368,19 @@ int launch_fixed(const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned n_tiles,
   if (!resident_dev[dev]) {
     int sms = 0, per_sm = 0;
     SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_accum_int_fixed_kernel<LP, IS_S8>, kT, smem));
+    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_accum_int_fixed_kernel<LP, VAR>, kT, smem));
     resident_dev[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
   const unsigned grid = n_tiles < (unsigned)resident_dev[dev] ? n_tiles : (unsigned)resident_dev[dev];
-  iqbb_accum_int_fixed_kernel<LP, IS_S8><<<grid, kT, smem, st>>>(a, taps);
+  iqbb_accum_int_fixed_kernel<LP, VAR><<<grid, kT, smem, st>>>(a, taps);
   SDRG_CHECK_LAUNCH("iqbb_accum_int_fixed_kernel");
   return SDRG_OK;
 }
 
-template <bool IS_S8>
+template <int VAR>
 int dispatch_fixed(int lp, const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned grid, cudaStream_t st) {
   switch (lp) {
-#define SDRG_CASE(N) case N: return launch_fixed<N, IS_S8>(a, taps, grid, st);
+#define SDRG_CASE(N) case N: return launch_fixed<N, VAR>(a, taps, grid, st);
     SDRG_CASE(2) SDRG_CASE(4) SDRG_CASE(6) SDRG_CASE(8) SDRG_CASE(10) SDRG_CASE(12) SDRG_CASE(14) SDRG_CASE(16)
     SDRG_CASE(18) SDRG_CASE(20) SDRG_CASE(22) SDRG_CASE(24) SDRG_CASE(26) SDRG_CASE(28) SDRG_CASE(30) SDRG_CASE(32)
 #undef SDRG_CASE
@@ -510,7 +521,8 @@ int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st) {
     IqbbTaps taps;
     for (int t = 0; t < 32; ++t) taps.t[t] = make_int4(0, 0, 0, 0);
     for (int t = 0; t < (int)a.taps_len; ++t) taps.t[pad + t] = ((const int4 *)a.host_taps)[t];
-    return scalar == SDRG_T_S8 ? dispatch_fixed<true>(lp, a, taps, grid, st) : dispatch_fixed<false>(lp, a, taps, grid, st);
+    if (scalar == SDRG_T_S8) return dispatch_fixed<1>(lp, a, taps, grid, st);
+    return a.in_fmt == 4 ? dispatch_fixed<2>(lp, a, taps, grid, st) : dispatch_fixed<0>(lp, a, taps, grid, st);
   }
   if (scalar == SDRG_T_F32) {
     const size_t smem = accum_smem_f32(a.taps_len, a.hist_len);
