@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
     // Complete interior window (the common case): every bound is a launch constant, so the chunk
     // arithmetic, the ragged-batch predicates and the tail addressing of the general path below fold
     // into a handful of instructions -- the kernel is issue-limited, not byte-limited, beyond ~85 %
-    // of HBM (profiles/r02_fold_probe.md).
+    // of HBM (profiles/r01_final_fold_probe.md).
     if (a.fast && id > 0 && (int)((id + 1) * a.ss) + win_off <= (int)a.n) {
       const int c_lo = (int)(id * a.ss) + win_off;
       const float2 *__restrict__ xc = x + c_lo + lane;
