@@ -19,6 +19,7 @@
 // (j div Ns) Ns R + (j mod Ns) + r Ns.  Twiddles come from a table of n-th roots of unity computed
 // in double on the host.  Data ping-pongs between shared-memory buffers; one __syncthreads per stage.
 #include "fft_kernels.cuh"
+#include <atomic>
 #include <cstdlib>
 
 namespace sdrg {
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
 int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st) {
   if (batch == 0) return SDRG_OK;
   const size_t smem = (size_t)2 * padded_len(n) * sizeof(float2);
-  static size_t attr[kMaxDevices] = {0};
+  static std::atomic<size_t> attr[kMaxDevices];
   const int dev = current_device();
   if (smem > 48 * 1024 && smem > attr[dev]) {
     SDRG_CUDA(cudaFuncSetAttribute(fft_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -387,7 +388,7 @@ int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
   if (n_blocks == 0) return SDRG_OK;
   const int n = 2 * a.block;
   const size_t smem = (size_t)3 * padded_len(n) * sizeof(float2);
-  static size_t attr[kMaxDevices] = {0};
+  static std::atomic<size_t> attr[kMaxDevices];
   const int dev = current_device();
   if (smem > 48 * 1024 && smem > attr[dev]) {
     SDRG_CUDA(cudaFuncSetAttribute(filter_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -397,7 +398,7 @@ int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
   static const int r16 = [] { const char *e = getenv("SDRG_FFT_R16"); return e ? atoi(e) : 1; }();
   if (n >= 512 && (a.n_filters == 1 || (r16 && a.spec))) {   // in-place stages on a single buffer (n == 16 * threads)
     const size_t smem1 = (size_t)padded_len(n) * sizeof(float2);
-    static size_t attr1[kMaxDevices] = {0};
+    static std::atomic<size_t> attr1[kMaxDevices];
     if (smem1 > 48 * 1024 && smem1 > attr1[dev]) {
       SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       SDRG_CUDA(cudaFuncSetAttribute(filter_ola1_r16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));

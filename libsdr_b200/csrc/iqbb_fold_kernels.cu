@@ -24,6 +24,7 @@
 // accumulators (finalized by iqbb_finalize_kernel); tails sent ahead are carried in registers into
 // the next window when the same warp processes it.
 #include "iqbb_kernels.cuh"
+#include <atomic>
 #include <cstdlib>
 
 namespace sdrg {
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
 
 template <int S, int P = 0>
 static int launch_fold_win_s(const IqbbFoldArgs &a, cudaStream_t st) {
-  static int resident_dev[kMaxDevices] = {0};
+  static std::atomic<int> resident_dev[kMaxDevices];
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
   const int dev = current_device();
   if (!resident_dev[dev]) {
@@ -711,7 +712,7 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   if (probe == 1) return launch_fold_probe<1>(a, st);
   if (probe == 2) return launch_fold_probe<2>(a, st);
   if (probe == 3) return launch_fold_probe<3>(a, st);
-  static int resident_dev[kMaxDevices] = {0};     // CTAs that fit the device at once: SMs x occupancy
+  static std::atomic<int> resident_dev[kMaxDevices];     // CTAs that fit the device at once: SMs x occupancy
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
   const int dev = current_device();
   if (!resident_dev[dev]) {
@@ -730,7 +731,7 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
 }
 
 static int launch_fold_tma(IqbbFoldArgs a, cudaStream_t st) {
-  static bool attr_set[kMaxDevices] = {false};
+  static std::atomic<bool> attr_set[kMaxDevices];
   const size_t smem = (size_t)kFoldWarps * kTmaRing * sizeof(float2);
   const int dev = current_device();
   if (!attr_set[dev]) {

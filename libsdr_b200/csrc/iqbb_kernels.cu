@@ -17,6 +17,7 @@
 // Kernel 2 (iqbb_finalize_*): one thread per completed window: division / narrowing, optional
 //   fused FM/AM/USB demodulation, carries the open window into the next call.
 #include "iqbb_kernels.cuh"
+#include <atomic>
 #include "demod_math.cuh"
 
 namespace sdrg {
@@ -363,7 +364,7 @@ int launch_fixed(const IqbbAccumArgs &a, const IqbbTaps &taps, unsigned n_tiles,
   constexpr int NV = (LP + 7 + 3) / 4;
   constexpr int xs_pitch = (kTile + 4 * NV + 8 + 3) & ~3;
   const size_t smem = sizeof(int2) * 128 + sizeof(int2) * kR * kZRow + sizeof(uint32_t) * 2 * xs_pitch;
-  static int resident_dev[kMaxDevices] = {0};      // per instantiation and device: CTAs that fit at once
+  static std::atomic<int> resident_dev[kMaxDevices];      // per instantiation and device: CTAs that fit at once
   const int dev = current_device();
   if (!resident_dev[dev]) {
     int sms = 0, per_sm = 0;
