@@ -159,13 +159,14 @@ __device__ float2 *fft_smem(float2 *a, float2 *b, float2 *c, const int n, const 
 // for n <= 8 * blockDim.
 template <int R, bool INV, int B>
 __device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const int n, const int Ns,
-                                              const float2 *__restrict__ tw, const float2 *__restrict__ mul) {
+                                              const float2 *__restrict__ tw, const float2 *__restrict__ mul,
+                                              const int tid, const int nthr) {
   const int nb = n / R;
   const int tstep = n / (Ns * R);
   float2 v[B][R];
 #pragma unroll
   for (int b = 0; b < B; ++b) {
-    const int j = threadIdx.x + b * blockDim.x;
+    const int j = tid + b * nthr;
     if (j < nb) {
       const int k = j & (Ns - 1);
 #pragma unroll
@@ -206,7 +207,7 @@ __device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const in
   __syncthreads();
 #pragma unroll
   for (int b = 0; b < B; ++b) {
-    const int j = threadIdx.x + b * blockDim.x;
+    const int j = tid + b * nthr;
     if (j < nb) {
       const int k = j & (Ns - 1);
       const int base = (j - k) * R + k;
@@ -224,9 +225,9 @@ __device__ void fft_smem_inplace(float2 *buf, const int n, const int log2n, cons
   bool first = true;
   while (left > 0) {
     const float2 *m = first ? mul : nullptr;
-    if (left >= 3 && left != 4) { stage_inplace<8, INV, EPT / 8>(buf, n, Ns, tw, m); Ns *= 8; left -= 3; }
-    else if (left >= 2) { stage_inplace<4, INV, EPT / 4>(buf, n, Ns, tw, m); Ns *= 4; left -= 2; }
-    else { stage_inplace<2, INV, EPT / 2>(buf, n, Ns, tw, m); Ns *= 2; left -= 1; }
+    if (left >= 3 && left != 4) { stage_inplace<8, INV, EPT / 8>(buf, n, Ns, tw, m, threadIdx.x, blockDim.x); Ns *= 8; left -= 3; }
+    else if (left >= 2) { stage_inplace<4, INV, EPT / 4>(buf, n, Ns, tw, m, threadIdx.x, blockDim.x); Ns *= 4; left -= 2; }
+    else { stage_inplace<2, INV, EPT / 2>(buf, n, Ns, tw, m, threadIdx.x, blockDim.x); Ns *= 2; left -= 1; }
     first = false;
   }
 }
@@ -234,14 +235,15 @@ __device__ void fft_smem_inplace(float2 *buf, const int n, const int log2n, cons
 // Stages for the middle `bits` bits of a transform whose first (forward) or last (inverse) radix-2
 // stage is fused into the global load / store: radix 16 while possible, then 8 / 4 / 2.
 template <bool INV>
-__device__ void fft_smem_inplace16(float2 *buf, const int n, int Ns, int left, const float2 *tw, const float2 *mul) {
+__device__ void fft_smem_inplace16(float2 *buf, const int n, int Ns, int left, const float2 *tw, const float2 *mul,
+                                   const int tid, const int nthr) {
   bool first = true;
   while (left > 0) {
     const float2 *m = first ? mul : nullptr;
-    if (left >= 4 && left != 5) { stage_inplace<16, INV, 1>(buf, n, Ns, tw, m); Ns *= 16; left -= 4; }
-    else if (left >= 3) { stage_inplace<8, INV, 2>(buf, n, Ns, tw, m); Ns *= 8; left -= 3; }
-    else if (left >= 2) { stage_inplace<4, INV, 4>(buf, n, Ns, tw, m); Ns *= 4; left -= 2; }
-    else { stage_inplace<2, INV, 8>(buf, n, Ns, tw, m); Ns *= 2; left -= 1; }
+    if (left >= 4 && left != 5) { stage_inplace<16, INV, 1>(buf, n, Ns, tw, m, tid, nthr); Ns *= 16; left -= 4; }
+    else if (left >= 3) { stage_inplace<8, INV, 2>(buf, n, Ns, tw, m, tid, nthr); Ns *= 8; left -= 3; }
+    else if (left >= 2) { stage_inplace<4, INV, 4>(buf, n, Ns, tw, m, tid, nthr); Ns *= 4; left -= 2; }
+    else { stage_inplace<2, INV, 8>(buf, n, Ns, tw, m, tid, nthr); Ns *= 2; left -= 1; }
     first = false;
   }
 }
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(512, 2) filter_ola1_r16_kernel(const FilterArg
       if (roll) ho[i] = c;
     }
     __syncthreads();
-    fft_smem_inplace16<false>(s0, n, 2, a.log2n - 1, tw, nullptr);
+    fft_smem_inplace16<false>(s0, n, 2, a.log2n - 1, tw, nullptr, threadIdx.x, blockDim.x);
   }
   if (MODE == 1) {
     float2 *X = (float2 *)a.spec + (size_t)b * n;
@@ -286,9 +288,9 @@ __global__ void __launch_bounds__(512, 2) filter_ola1_r16_kernel(const FilterArg
     const float2 *X = (const float2 *)a.spec + (size_t)b * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s0[pidx(i)] = cmulf(X[i], __ldg(K + i));
     __syncthreads();
-    fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, nullptr);
+    fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, nullptr, threadIdx.x, blockDim.x);
   } else {
-    fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, K);
+    fft_smem_inplace16<true>(s0, n, 1, a.log2n - 1, tw, K, threadIdx.x, blockDim.x);
   }
   const float sc = 1.0f / (float)n;
   float2 *o = (float2 *)a.out + (size_t)f * a.out_stride + (size_t)b * N;
@@ -336,6 +338,40 @@ __global__ void __launch_bounds__(1024) fft_batch_kernel(const float2 *__restric
   for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = r[pidx(i)];
 }
 
+// Radix-16 in-place plan for the plain transform (n >= 256): n/16 threads per transform, several
+// transforms per CTA when n is small; an odd log2 n sheds its radix-2 stage into the global load
+// (Stockham DIT first stage, Ns = 1, no twiddles), so n = 8192 costs three shared-memory passes.
+template <bool INV>
+__global__ void __launch_bounds__(512, 2) fft_batch_r16_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, const int n,
+                                                                const int log2n, const int batch, const float2 *__restrict__ tw) {
+  extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+  const int tpf = n >> 4;                                  // threads per transform
+  const int fpc = blockDim.x / tpf;                        // transforms per CTA
+  const int g = threadIdx.x / tpf, tid = threadIdx.x - g * tpf;
+  int f = blockIdx.x * fpc + g;
+  const bool live = f < batch;
+  if (!live) f = batch - 1;                                // keeps the barriers uniform; the result is not stored
+  float2 *s0 = (float2 *)fft_smem_raw + (size_t)g * padded_len(n);
+  const float2 *x = in + (size_t)f * n;
+  int Ns = 1, left = log2n;
+  if (log2n & 1) {
+    const int h = n >> 1;
+    for (int i = tid; i < h; i += tpf) {
+      const float2 p = x[i], c = x[i + h];
+      s0[pidx(2 * i)] = caddf(p, c);
+      s0[pidx(2 * i + 1)] = csubf(p, c);
+    }
+    Ns = 2; left -= 1;
+  } else {
+    for (int i = tid; i < n; i += tpf) s0[pidx(i)] = x[i];
+  }
+  __syncthreads();
+  fft_smem_inplace16<INV>(s0, n, Ns, left, tw, nullptr, tid, tpf);
+  if (!live) return;
+  float2 *y = out + (size_t)f * n;
+  for (int i = tid; i < n; i += tpf) y[i] = s0[pidx(i)];
+}
+
 // ---- fused overlap-save filter bank -----------------------------------------------------------------
 // CTA b: X = FFT_2N([block b-1 | block b]); for every filter f: y = IFFT_2N(X K_f); out_f[block b] =
 // y[N..2N) / 2N.  Block -1 is the carried history (the last N samples of the previous call).
@@ -371,6 +407,23 @@ __global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
 
 int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st) {
   if (batch == 0) return SDRG_OK;
+  static const int r16 = [] { const char *e = getenv("SDRG_FFT_R16"); return e ? atoi(e) : 1; }();
+  if (r16 && n >= 256 && batch <= 0x7fffffffull) {
+    const int tpf = n / 16, fpc = tpf >= 256 ? 1 : 256 / tpf;
+    const size_t smem = (size_t)fpc * padded_len(n) * sizeof(float2);
+    static std::atomic<size_t> attr16[kMaxDevices];
+    const int dev = current_device();
+    if (smem > 48 * 1024 && smem > attr16[dev]) {
+      SDRG_CUDA(cudaFuncSetAttribute(fft_batch_r16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SDRG_CUDA(cudaFuncSetAttribute(fft_batch_r16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr16[dev] = smem;
+    }
+    const unsigned grid = (unsigned)((batch + fpc - 1) / fpc);
+    if (inverse) fft_batch_r16_kernel<true><<<grid, tpf * fpc, smem, st>>>((const float2 *)in, (float2 *)out, n, log2n, (int)batch, (const float2 *)tw);
+    else fft_batch_r16_kernel<false><<<grid, tpf * fpc, smem, st>>>((const float2 *)in, (float2 *)out, n, log2n, (int)batch, (const float2 *)tw);
+    SDRG_CHECK_LAUNCH("fft_batch_r16_kernel");
+    return SDRG_OK;
+  }
   const size_t smem = (size_t)2 * padded_len(n) * sizeof(float2);
   static std::atomic<size_t> attr[kMaxDevices];
   const int dev = current_device();
