@@ -157,10 +157,15 @@ __device__ float2 *fft_smem(float2 *a, float2 *b, float2 *c, const int n, const 
 // of one, half the shared memory -> two resident CTAs of 1024 threads per SM for the 8192-point
 // transform).  B = butterflies per thread (n/R/blockDim), at most 8/R * 8... kept <= 8 elements/thread
 // for n <= 8 * blockDim.
-template <int R, bool INV, int B>
+// SRC_G: the inputs come straight from global memory `gin` (natural order, coalesced: consecutive threads read
+// consecutive j) -- nothing in `buf` is live, so the barrier between the read and the write phase is dropped.
+// DST_G: the outputs go straight to global memory `gout`; legal for the LAST stage only, where Ns = n/R makes the
+// output index j + r n/R coalesced as well.
+template <int R, bool INV, int B, bool SRC_G = false, bool DST_G = false>
 __device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const int n, const int Ns,
                                               const float2 *__restrict__ tw, const float2 *__restrict__ mul,
-                                              const int tid, const int nthr) {
+                                              const int tid, const int nthr,
+                                              const float2 *__restrict__ gin = nullptr, float2 *__restrict__ gout = nullptr) {
   const int nb = n / R;
   const int tstep = n / (Ns * R);
   float2 v[B][R];
@@ -171,7 +176,7 @@ __device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const in
       const int k = j & (Ns - 1);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        v[b][r] = buf[pidx(j + r * nb)];
+        v[b][r] = SRC_G ? gin[j + r * nb] : buf[pidx(j + r * nb)];
         if (mul) v[b][r] = cmulf(v[b][r], __ldg(mul + j + r * nb));
       }
       if (k > 0) {
@@ -204,7 +209,7 @@ __device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const in
       else dft16<INV>(v[b]);
     }
   }
-  __syncthreads();
+  if (!SRC_G) __syncthreads();
 #pragma unroll
   for (int b = 0; b < B; ++b) {
     const int j = tid + b * nthr;
@@ -212,10 +217,13 @@ __device__ __forceinline__ void stage_inplace(float2 *__restrict__ buf, const in
       const int k = j & (Ns - 1);
       const int base = (j - k) * R + k;
 #pragma unroll
-      for (int r = 0; r < R; ++r) buf[pidx(base + r * Ns)] = v[b][r];
+      for (int r = 0; r < R; ++r) {
+        if (DST_G) gout[base + r * Ns] = v[b][r];
+        else buf[pidx(base + r * Ns)] = v[b][r];
+      }
     }
   }
-  __syncthreads();
+  if (!DST_G) __syncthreads();
 }
 
 // n = EPT * blockDim.x points: EPT/8 radix-8, EPT/4 radix-4 or EPT/2 radix-2 butterflies per thread
@@ -350,26 +358,30 @@ __global__ void __launch_bounds__(512, 2) fft_batch_r16_kernel(const float2 *__r
   const int g = threadIdx.x / tpf, tid = threadIdx.x - g * tpf;
   int f = blockIdx.x * fpc + g;
   const bool live = f < batch;
-  if (!live) f = batch - 1;                                // keeps the barriers uniform; the result is not stored
+  if (!live) f = batch - 1;                                // keeps the barriers uniform; the result goes to a dummy row
   float2 *s0 = (float2 *)fft_smem_raw + (size_t)g * padded_len(n);
   const float2 *x = in + (size_t)f * n;
-  int Ns = 1, left = log2n;
-  if (log2n & 1) {
-    const int h = n >> 1;
-    for (int i = tid; i < h; i += tpf) {
-      const float2 p = x[i], c = x[i + h];
-      s0[pidx(2 * i)] = caddf(p, c);
-      s0[pidx(2 * i + 1)] = csubf(p, c);
+  float2 *y = live ? out + (size_t)f * n : s0;             // dead groups "store" into their own shared buffer (never read again)
+  // first stage: radix 16 straight from global memory (Ns = 1: no twiddles), 16 independent loads per thread
+  stage_inplace<16, INV, 1, true, false>(s0, n, 1, tw, nullptr, tid, tpf, x, nullptr);
+  int Ns = 16, left = log2n - 4;
+  // middle stages in shared memory; the last one writes straight to global memory
+  while (left > 0) {
+    if (left >= 4) {                                       // 16 while possible; the remainder (8, 4 or 2) is the last stage
+      if (left == 4) stage_inplace<16, INV, 1, false, true>(s0, n, Ns, tw, nullptr, tid, tpf, nullptr, y);
+      else stage_inplace<16, INV, 1>(s0, n, Ns, tw, nullptr, tid, tpf);
+      Ns *= 16; left -= 4;
+    } else if (left == 3) {
+      stage_inplace<8, INV, 2, false, true>(s0, n, Ns, tw, nullptr, tid, tpf, nullptr, y);
+      Ns *= 8; left -= 3;
+    } else if (left == 2) {
+      stage_inplace<4, INV, 4, false, true>(s0, n, Ns, tw, nullptr, tid, tpf, nullptr, y);
+      Ns *= 4; left -= 2;
+    } else {
+      stage_inplace<2, INV, 8, false, true>(s0, n, Ns, tw, nullptr, tid, tpf, nullptr, y);
+      Ns *= 2; left -= 1;
     }
-    Ns = 2; left -= 1;
-  } else {
-    for (int i = tid; i < n; i += tpf) s0[pidx(i)] = x[i];
   }
-  __syncthreads();
-  fft_smem_inplace16<INV>(s0, n, Ns, left, tw, nullptr, tid, tpf);
-  if (!live) return;
-  float2 *y = out + (size_t)f * n;
-  for (int i = tid; i < n; i += tpf) y[i] = s0[pidx(i)];
 }
 
 // ---- fused overlap-save filter bank -----------------------------------------------------------------
