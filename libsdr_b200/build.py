@@ -22,25 +22,52 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hh"))] + \
+           [os.path.join(HERE, "..", "include", "sdrg.h")]
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "sdrg.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in sources() + _headers())
 
 
 def build(force=False, verbose=False):
+    """Every source is compiled to its own object (in parallel, and only when it or a header changed),
+    then the objects are linked into libsdrg.so."""
     if not force and not needs_build():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "..", "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
     extra = os.environ.get("SDRG_NVCC_EXTRA", "").split()
-    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    stamp = os.path.join(objdir, "flags.txt")
+    same_flags = os.path.exists(stamp) and open(stamp).read() == " ".join(flags)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        if not force and same_flags and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, None
+        r = subprocess.run(["nvcc"] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+        return obj, r
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
+    for obj, r in results:
+        if r is not None and r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed compiling " + obj)
+        if r is not None and verbose:
+            sys.stderr.write(r.stderr)
+    open(stamp, "w").write(" ".join(flags))
+    r = subprocess.run(["nvcc"] + NVCC_FLAGS + ["-o", OUT] + [o for o, _ in results], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libsdrg.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libsdrg.so")
     return OUT
 
 
