@@ -117,7 +117,7 @@ int sdrg_iqbb_design(sdrg_iqbb *h, const sdrg_config *src, sdrg_config *out);
 int sdrg_iqbb_set_input_type(sdrg_iqbb *h, int type);
 
 /* SDRG_T_F32 only: which accumulate kernel config() selects.  0 = auto (folded when
- * sub_sample >= max(32, order-1), else direct), 1 = direct (sample-by-sample FIR, FMA-bound),
+ * sub_sample >= max(2, order-1), else direct), 1 = direct (sample-by-sample FIR, FMA-bound),
  * 2 = folded (one weight per input sample, HBM-bound; SDRG_ERR_CONFIG at config() if not eligible),
  * 3 = folded with TMA bulk-copy staging through shared memory (experimental; same results).
  * Must be called before config(). */

@@ -184,9 +184,9 @@ int upload_fold_tables(sdrg_iqbb *h) {
   const IqbbDesign &d = h->d;
   free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
   const size_t L = d.order, ss = d.sub_sample;
-  const bool eligible = d.scalar == SDRG_T_F32 && ss >= 32 && ss + 1 >= L;
+  const bool eligible = d.scalar == SDRG_T_F32 && ss >= 2 && ss + 1 >= L;
   if (h->float_path >= 2 && !eligible && d.scalar == SDRG_T_F32)
-    return set_error(SDRG_ERR_CONFIG, "IQBaseBand<float>: folded path needs sub_sample >= max(32, order-1) (ss=%zu, order=%zu)", ss, L);
+    return set_error(SDRG_ERR_CONFIG, "IQBaseBand<float>: folded path needs sub_sample >= max(2, order-1) (ss=%zu, order=%zu)", ss, L);
   h->fold = eligible && h->float_path != 1;
   if (!h->fold) return SDRG_OK;
   const bool nco = d.lut_inc != 0, neg = d.negative;

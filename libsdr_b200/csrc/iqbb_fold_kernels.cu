@@ -563,6 +563,125 @@ static int launch_fold_win(const IqbbFoldArgs &a, cudaStream_t st) {
   }
 }
 
+// ---- short windows (2 <= ss < 128) ------------------------------------------------------------------
+// With few samples per window the per-window cost of the residue scheme above (eight H_u products, the
+// tail set-up, two staged rows) dominates, so here every sample gets its complete weight instead:
+//     own window   z_o = (G(p) - T_e(p)) x[p],   G = A(a_p) U(r_p, 0)
+//     next window  z_n = T_e(p) x[p]   for the last L-1 samples of a window,  T_e = A(a_b) U(r_b, e), phase_b = phase_p + e inc
+// (two table lookups and two complex products per sample, one more pair on tail samples).  The weighted
+// samples of a 2048-sample tile are staged in shared memory and summed per window by 1, 2 or 4 threads,
+// like the integer kernels do.  Loads are coalesced 8-byte streams, 8 per thread in flight.
+constexpr int kSmallTile = 2048;
+
+__global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_small_kernel(const IqbbFoldArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ float2 sA[128];
+  __shared__ float2 sH[256];
+  float2 *zo = (float2 *)dyn_smem, *zn = zo + kSmallTile;
+  const int tid = threadIdx.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + tid; k < a.zero_next; k += gridDim.x * blockDim.x)
+    ((float2 *)a.acc_next)[k] = make_float2(0.f, 0.f);
+  if (tid < 128) sA[tid] = a.tab_a[tid];
+  sH[tid] = a.tab_u[(size_t)tid * a.taps_len];
+  __syncthreads();
+
+  const float2 *__restrict__ x = (const float2 *)a.x;
+  float *acc = (float *)a.acc_cur;
+  const uint32_t ss = a.ss, L = a.taps_len, L1 = L - 1;
+  const uint64_t magic = ((1ull << 40) + ss - 1) / ss;     // q / ss == (q * magic) >> 40 for q < 2^31, ss < 2^9
+  const int win_off = (int)a.first - (int)a.r0;            // begin(s) = s*ss + win_off (s>0), end(s) = (s+1)*ss + win_off
+  const int gsh = ss >= 32 ? 2 : (ss >= 16 ? 1 : 0), G = 1 << gsh, sub = tid & (G - 1);
+  const uint32_t n_tiles = (a.n + kSmallTile - 1) / kSmallTile;
+  const uint32_t d256 = 256u % ss, inc256 = 256u * a.inc;
+
+  float2 xv[8];
+  auto load_tile = [&](uint32_t t) {                         // 8 coalesced streaming loads per thread
+    const uint32_t b0 = t * kSmallTile, hi = min(a.n - b0, (uint32_t)kSmallTile);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t o = tid + 256 * r;
+      xv[r] = make_float2(0.f, 0.f);
+      if (o < hi) xv[r] = ld_stream(x + b0 + o);
+    }
+  };
+  if (blockIdx.x < n_tiles) load_tile(blockIdx.x);
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint32_t base = t * kSmallTile;
+    const uint32_t t_hi = min(a.n - base, (uint32_t)kSmallTile);
+    // position inside its window of this thread's first sample (one division per tile), then +256 per step
+    const uint32_t p0 = base + tid;
+    const uint32_t q0 = a.r0 + p0 - ((a.first && p0 > 0) ? 1u : 0u);
+    uint32_t m = q0 - (uint32_t)(((uint64_t)q0 * magic) >> 40) * ss;
+    if (a.first && p0 == 0) m = ss - 1;                       // q(0) = q(1) = 0: sample 0 counts as position -1 (its e is set below)
+    uint32_t ph = a.phase0 + p0 * a.inc;                      // bits 0..14 are the phase
+#pragma unroll
+    for (int r = 0; r < 8; ++r, ph += inc256) {
+      const uint32_t o = tid + 256 * r;
+      float2 vo = make_float2(0.f, 0.f), vn = vo;
+      if (o < t_hi) {
+        float2 g = cmul(sA[(ph & 0x7fffu) >> 8], sH[ph & 255u]);
+        uint32_t e = ss - m;                                  // samples up to and including the window's last one
+        if (a.first && base + o == 0) e = ss + 1;             // the extra first sample of window 0
+        if (e <= L1) {
+          const uint32_t pb = ph + e * a.inc;                 // phase of the next window's first sample
+          const float2 tw = cmul(sA[(pb & 0x7fffu) >> 8], __ldg(a.tab_u + (size_t)(pb & 255u) * L + e));
+          vn = cmul(tw, xv[r]);
+          g.x -= tw.x; g.y -= tw.y;
+        }
+        vo = cmul(g, xv[r]);
+      }
+      m += d256; if (m >= ss) m -= ss;                        // (m + 256) mod ss, d256 = 256 mod ss
+      zo[o] = vo; zn[o] = vn;
+    }
+    __syncthreads();
+    if (t + gridDim.x < n_tiles) load_tile(t + gridDim.x);     // in flight while the windows of this tile are summed
+    // per-window sums of the tile: G threads per window (outer bound CTA-uniform)
+    {
+      const uint32_t q_lo = a.r0 + base - ((a.first && base > 0) ? 1u : 0u);
+      const uint32_t q_hi = a.r0 + (base + t_hi - 1) - ((a.first && base + t_hi - 1 > 0) ? 1u : 0u);
+      const uint32_t slot_lo = (uint32_t)(((uint64_t)q_lo * magic) >> 40), slot_hi = (uint32_t)(((uint64_t)q_hi * magic) >> 40);
+      for (uint32_t sb = slot_lo; sb <= slot_hi; sb += kFoldThreads >> gsh) {
+        const uint32_t sl = sb + (uint32_t)(tid >> gsh);
+        float sr = 0.f, si = 0.f, tr = 0.f, ti = 0.f;
+        if (sl <= slot_hi) {
+          const int64_t wb = sl == 0 ? 0 : (int64_t)sl * ss + win_off, we = (int64_t)(sl + 1) * ss + win_off;
+          const int lo = (int)max(wb - (int64_t)base, (int64_t)0), hi = (int)min(we - (int64_t)base, (int64_t)t_hi);
+          for (int o = lo + sub; o < hi; o += G) { const float2 z = zo[o]; sr += z.x; si += z.y; }
+          const int tl = (int)max((int64_t)lo, we - (int64_t)L1 - (int64_t)base);
+          for (int o = tl + sub; o < hi; o += G) { const float2 z = zn[o]; tr += z.x; ti += z.y; }
+        }
+        for (int d = G >> 1; d > 0; d >>= 1) {
+          sr += __shfl_xor_sync(kFull, sr, d); si += __shfl_xor_sync(kFull, si, d);
+          tr += __shfl_xor_sync(kFull, tr, d); ti += __shfl_xor_sync(kFull, ti, d);
+        }
+        if (sub == 0 && sl <= slot_hi) {
+          if (sr != 0.f || si != 0.f) { atomicAdd(acc + 2 * (size_t)sl, sr); atomicAdd(acc + 2 * (size_t)sl + 1, si); }
+          if (tr != 0.f || ti != 0.f) { atomicAdd(acc + 2 * (size_t)sl + 2, tr); atomicAdd(acc + 2 * (size_t)sl + 3, ti); }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_fold_small(const IqbbFoldArgs &a, cudaStream_t st) {
+  static std::atomic<int> resident_dev[kMaxDevices];
+  const size_t smem = (size_t)2 * kSmallTile * sizeof(float2);
+  const int dev = current_device();
+  if (!resident_dev[dev]) {
+    SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0, per_sm = 0;
+    SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_f32_small_kernel, kFoldThreads, smem));
+    resident_dev[dev] = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const uint64_t n_tiles = ((uint64_t)a.n + kSmallTile - 1) / kSmallTile;
+  const uint64_t resident = (uint64_t)resident_dev[dev];
+  iqbb_fold_f32_small_kernel<<<(unsigned)(n_tiles < resident ? n_tiles : resident), kFoldThreads, smem, st>>>(a);
+  SDRG_CHECK_LAUNCH("iqbb_fold_f32_small_kernel");
+  return SDRG_OK;
+}
+
 // ---- bandwidth probes (SDRG_FOLD_PROBE=1..3; results are NOT the IQBaseBand output) ---------------
 // Same persistent grid, chunk dealing and staging as iqbb_fold_f32_kernel with the arithmetic reduced
 // to one complex add per sample: what the access pattern itself can reach.  MODE 1: batches of 8 steps
@@ -708,6 +827,8 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   }
   static const int win_env = [] { const char *e = getenv("SDRG_FOLD_WIN"); return e ? atoi(e) : 1; }();
   static const int probe = [] { const char *e = getenv("SDRG_FOLD_PROBE"); return e ? atoi(e) : 0; }();
+  static const int small_env = [] { const char *e = getenv("SDRG_FOLD_SMALL"); return e ? atoi(e) : 55; }();   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
+  if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) return launch_fold_small(a, st);
   if (!probe && win_env && a.fast && a.ss <= 512 && a.fast_hi >= 1) return launch_fold_win(a, st);
   if (probe == 1) return launch_fold_probe<1>(a, st);
   if (probe == 2) return launch_fold_probe<2>(a, st);
@@ -757,7 +878,7 @@ int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st) {
   const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0;
   static const int env_variant = [] { const char *e = getenv("SDRG_FOLD_VARIANT"); return e ? atoi(e) : 0; }();
   const int variant = a.variant ? (int)a.variant : env_variant;      // 2 = TMA staging (experimental)
-  return (aligned && variant == 2) ? launch_fold_tma(a, st) : launch_fold_ldg(a, st);
+  return (aligned && variant == 2 && a.ss >= 32) ? launch_fold_tma(a, st) : launch_fold_ldg(a, st);
 }
 
 }  // namespace sdrg

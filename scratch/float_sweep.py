@@ -11,6 +11,8 @@ cases = [(int(a.split(",")[0]), int(a.split(",")[1])) for a in sys.argv[1:]] or 
          (20000, 64), (416, 15), (416, 100), (1000, 100)]
 for ss, order in cases:
     bb = IQBaseBand("f32", 100e3, 100e3, 12.5e3, order, ss, 0.0)
+    import os
+    if os.environ.get("FLOAT_PATH"): bb.setFloatPath(int(os.environ["FLOAT_PATH"]))
     bb.config(sample_rate=20e6, buffer_size=n)
     for _ in range(3):
         bb.process(x)
