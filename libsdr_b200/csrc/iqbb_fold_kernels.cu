@@ -23,159 +23,11 @@
 // chunk end the warp reduces with shuffles and issues one RED.ADD per component into the per-call
 // accumulators (finalized by iqbb_finalize_kernel); tails sent ahead are carried in registers into
 // the next window when the same warp processes it.
-#include "iqbb_kernels.cuh"
-#include <atomic>
-#include <cstdlib>
+#include "iqbb_fold_common.cuh"
 
 namespace sdrg {
+using namespace foldk;
 namespace {
-
-constexpr unsigned kFull = 0xffffffffu;
-constexpr int kFoldThreads = 256;
-constexpr int kFoldWarps = kFoldThreads / 32;
-
-__device__ __forceinline__ float2 ld_stream(const float2 *p) {
-  float2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-}
-// bulk L2 prefetch of [p, p + bytes): one instruction, no registers held while the data is in flight
-__device__ __forceinline__ void prefetch_l2(const float2 *lo, const float2 *hi) {
-  const uintptr_t a = (reinterpret_cast<uintptr_t>(lo) + 15) & ~uintptr_t(15);
-  const uintptr_t b = reinterpret_cast<uintptr_t>(hi) & ~uintptr_t(15);
-  if (b > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)(b - a)) : "memory");
-}
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ void cfma(float2 &acc, float2 w, float2 x) {
-  acc.x = fmaf(w.x, x.x, acc.x); acc.x = fmaf(-w.y, x.y, acc.x);
-  acc.y = fmaf(w.x, x.y, acc.y); acc.y = fmaf(w.y, x.x, acc.y);
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-  return v;
-}
-__device__ __forceinline__ void flush(float *acc, uint32_t slot, float2 v, int lane) {
-  const float sr = warp_sum(v.x), si = warp_sum(v.y);
-  if (lane == 0 && (sr != 0.f || si != 0.f)) { atomicAdd(acc + 2 * (size_t)slot, sr); atomicAdd(acc + 2 * (size_t)slot + 1, si); }
-}
-
-// Per-warp staging of window partials: row w holds the 32 per-lane partial sums of the w-th window
-// this warp finished; once 32 rows are full lane l sums row l (one LDS.64 per element, rows padded
-// to 33 to stay conflict free) and issues the RED.ADDs for its window.  This replaces a 5-step
-// shuffle reduction per component per window by ~3 instructions per window.
-constexpr int kStageRows = 16, kStagePitch = 33;
-
-struct WarpStage {
-  float2 *rows;      // [kStageRows][kStagePitch]
-  uint32_t my_slot;  // lane l: slot of row l
-  uint32_t count;
-  __device__ __forceinline__ void push(float2 v, uint32_t slot, int lane, float *acc_out) {
-    rows[count * kStagePitch + lane] = v;
-    if ((uint32_t)lane == count) my_slot = slot;
-    if (++count == kStageRows) drain(lane, acc_out);
-  }
-  __device__ __forceinline__ void drain(int lane, float *acc_out) {
-    __syncwarp();
-    if ((uint32_t)lane < count) {
-      float sr = 0.f, si = 0.f;
-      const float2 *r = rows + lane * kStagePitch;
-#pragma unroll 8
-      for (int i = 0; i < 32; ++i) { const float2 v = r[i]; sr += v.x; si += v.y; }   // the 32 lane partials of row `lane`
-      if (sr != 0.f || si != 0.f) { atomicAdd(acc_out + 2 * (size_t)my_slot, sr); atomicAdd(acc_out + 2 * (size_t)my_slot + 1, si); }
-    }
-    __syncwarp();
-    count = 0;
-  }
-};
-
-// chunk id -> (slot, first sample, length, tail start); false for an empty piece
-struct Chunk { uint32_t s; int c_lo, len, t_lo, full_end; };
-__device__ __forceinline__ bool chunk_of(const IqbbFoldArgs &a, uint32_t id, int win_off, int L1, Chunk &c) {
-  const uint32_t s = a.cpw == 1 ? id : id / a.cpw, part = a.cpw == 1 ? 0u : id % a.cpw;
-  c.s = s;
-  c.full_end = (int)((s + 1) * a.ss) + win_off;                          // exclusive, may exceed n
-  const int w_lo = s == 0 ? 0 : (int)(s * a.ss) + win_off;
-  const int w_hi = min(c.full_end, (int)a.n);
-  c.c_lo = w_lo + (int)(part * a.part);
-  if (c.c_lo >= w_hi) return false;
-  c.len = min(c.c_lo + (int)a.part, w_hi) - c.c_lo;
-  c.t_lo = max(0, min(c.len, c.full_end - L1 - c.c_lo));                 // samples >= t_lo send a tail ahead
-  return true;
-}
-
-// One chunk on the general path: any clipping, any piece of a long window, any tap count.
-__device__ __forceinline__ void fold_chunk_general(const IqbbFoldArgs &a, const uint32_t id, const uint32_t total_warps,
-                                                   const float2 *__restrict__ x, const float2 *sA, const float2 *sH,
-                                                   const int lane, const int L1, const int win_off,
-                                                   const uint32_t inc32, const uint32_t inc256,
-                                                   WarpStage &stage, float *acc_out) {
-    Chunk c;
-    if (lane == 0 && a.pf_dist && id + a.pf_dist * total_warps < a.n_chunks) {   // a later chunk of this warp -> L2, one instruction
-      Chunk nx;
-      if (chunk_of(a, id + a.pf_dist * total_warps, win_off, L1, nx)) prefetch_l2(x + nx.c_lo, x + nx.c_lo + nx.len);
-    }
-    if (!chunk_of(a, id, win_off, L1, c)) return;
-    const int len = c.len;
-    uint32_t ph = (a.phase0 + (uint32_t)(c.c_lo + lane) * a.inc) & 0x7fffu;         // this lane's phase in step 0
-    const uint32_t r0 = ph & 255u;        // low phase byte in step 0; step u has (r0 + u*inc32) & 255 in every batch
-    float2 R[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
-    const float2 *__restrict__ xc = x + c.c_lo + lane;
-
-    // every sample: R_u += A(a_p) x[p]   (its full weight G = H_u A)
-    int k = 0;
-    for (; k + 256 <= len; k += 256, ph = (ph + inc256) & 0x7fffu) {
-      float2 xv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) xv[u] = ld_stream(xc + k + 32 * u);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
-    }
-    // The last L-1 samples of the window also owe T_e x to the next window.  Their loads (a re-read
-    // of x, L2 resident, and the U(r_b, e) row) are issued together with the ragged batch so that
-    // the window costs two memory round trips, not three.
-    float2 sent = make_float2(0.f, 0.f);
-    const bool has_tail = c.t_lo < len;
-    const int jt = c.t_lo + lane;                                   // this lane's first tail sample
-    float2 Ab = make_float2(0.f, 0.f), xt0 = Ab, xt1 = Ab, ut0 = Ab, ut1 = Ab;
-    const float2 *__restrict__ ue = a.tab_u;
-    if (has_tail) {
-      const uint32_t pb = (a.phase0 + (uint32_t)c.full_end * a.inc) & 0x7fffu;
-      Ab = sA[pb >> 8];
-      ue = a.tab_u + (size_t)(pb & 255u) * a.taps_len + (c.full_end - c.c_lo - lane);   // U(r_b, e), e = end - j
-      if (jt < len) { xt0 = __ldg(xc + (jt - lane)); ut0 = __ldg(ue - (jt - lane)); }
-      if (jt + 32 < len) { xt1 = __ldg(xc + (jt + 32 - lane)); ut1 = __ldg(ue - (jt + 32 - lane)); }
-    }
-    if (k < len) {                        // ragged last batch
-      const int rem = len - k;
-      float2 xv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        xv[u] = make_float2(0.f, 0.f);
-        if (32 * u < rem && 32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (32 * u >= rem) break;
-        cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
-      }
-    }
-    if (has_tail) {
-      cfma(sent, cmul(Ab, ut0), xt0);     // zero when this lane has no such sample
-      cfma(sent, cmul(Ab, ut1), xt1);
-      for (int j = jt + 64; j < len; j += 32)       // L > 65 only
-        cfma(sent, cmul(Ab, __ldg(ue - (j - lane))), __ldg(xc + (j - lane)));
-    }
-    float2 tot = make_float2(-sent.x, -sent.y);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);   // H_u = U(r_u, 0)
-    stage.push(tot, c.s, lane, acc_out);
-    if (c.t_lo < len) stage.push(sent, c.s + 1, lane, acc_out);
-}
 
 // Ragged batch of a complete window: RS steps, only the last one predicated (per-lane constant).
 template <int RS>
@@ -274,160 +126,6 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
   stage.drain(lane, acc_out);
 
 }
-
-// ---- TMA variant ---------------------------------------------------------------------------------
-// Same arithmetic, different data movement: every warp owns a contiguous, 2 KB-aligned segment of
-// the call and streams it through a private shared-memory ring of kTmaTiles x 2 KB tiles filled by
-// 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) that complete on per-tile mbarriers.  Bytes in
-// flight no longer cost registers: 3 CTAs x 8 warps x 3 tiles x 2 KB = 144 KB per SM are outstanding
-// while the warps compute from shared memory.  No cross-warp synchronisation after the prologue.
-constexpr int kTmaTile = 256;                   // samples per tile (2 KB)
-constexpr int kTmaTiles = 4;                    // ring depth per warp
-constexpr int kTmaRing = kTmaTile * kTmaTiles;  // samples per ring
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
-}
-
-__global__ void __launch_bounds__(kFoldThreads, 3) iqbb_fold_f32_tma_kernel(const IqbbFoldArgs a) {
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  __shared__ float2 sA[128];
-  __shared__ float2 sH[256];
-  __shared__ __align__(8) unsigned long long bars[kFoldWarps][kTmaTiles];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (uint32_t k = blockIdx.x * blockDim.x + tid; k < a.zero_next; k += gridDim.x * blockDim.x)
-    ((float2 *)a.acc_next)[k] = make_float2(0.f, 0.f);
-  if (tid < 128) sA[tid] = a.tab_a[tid];
-  sH[tid] = a.tab_u[(size_t)tid * a.taps_len];
-  if (lane == 0) {
-#pragma unroll
-    for (int t = 0; t < kTmaTiles; ++t) mbar_init(smem_u32(&bars[warp][t]), 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  const uint64_t seg_lo64 = ((uint64_t)blockIdx.x * kFoldWarps + warp) * a.seg;
-  if (seg_lo64 >= a.n) return;
-  const uint32_t S_lo = (uint32_t)seg_lo64;
-  const uint32_t S_hi = (uint32_t)min((uint64_t)a.n, seg_lo64 + a.seg);
-  const float2 *__restrict__ x = (const float2 *)a.x;
-  float2 *ring = (float2 *)dyn_smem + (size_t)warp * kTmaRing;
-  const uint32_t ring_u32 = smem_u32(ring), bar_u32 = smem_u32(&bars[warp][0]);
-  const uint32_t n_tiles = (S_hi - S_lo + kTmaTile - 1) / kTmaTile;
-
-  // producer side (lane 0): tile t -> ring slot t % kTmaTiles
-  auto issue = [&](uint32_t t) {
-    const uint32_t start = S_lo + t * kTmaTile;
-    const uint32_t cnt = min((uint32_t)kTmaTile, S_hi - start);
-    const uint32_t bytes16 = (cnt * 8u) & ~15u;
-    const uint32_t slot = t % kTmaTiles;
-    mbar_expect_tx(bar_u32 + slot * 8, bytes16);
-    if (bytes16) tma_load_1d(ring_u32 + slot * (kTmaTile * 8), x + start, bytes16, bar_u32 + slot * 8);
-    if (cnt & 1u) ring[slot * kTmaTile + cnt - 1] = x[start + cnt - 1];     // odd tail of the call
-  };
-  if (lane == 0) {
-    for (uint32_t t = 0; t < min(n_tiles, (uint32_t)kTmaTiles); ++t) issue(t);
-  }
-  __syncwarp();
-  uint32_t landed = 0;      // tiles [0, landed) are known to be in shared memory
-  uint32_t issued = min(n_tiles, (uint32_t)kTmaTiles);
-
-  float *acc_out = (float *)a.acc_cur;
-  const int L1 = (int)a.taps_len - 1;
-  const int64_t win_off = (int64_t)a.first - (int64_t)a.r0;
-  const uint32_t inc32 = (32u * a.inc) & 0x7fffu, inc256 = (256u * a.inc) & 0x7fffu;
-
-  float2 base = make_float2(0.f, 0.f);
-  uint32_t base_slot = 0;
-  uint32_t s = (uint32_t)(((uint64_t)a.r0 + S_lo - ((a.first && S_lo > 0) ? 1u : 0u)) / a.ss);
-  for (uint32_t pos = S_lo; pos < S_hi; ++s) {
-    const int64_t full_end = (int64_t)((uint64_t)(s + 1) * a.ss) + win_off;
-    const uint32_t c_lo = pos;
-    const uint32_t c_hi = (uint32_t)min(full_end, (int64_t)S_hi);
-    const uint32_t len = c_hi - c_lo;
-    const int64_t t_lo64 = full_end - L1 - (int64_t)c_lo;
-    const uint32_t t_lo = t_lo64 < 0 ? 0u : (t_lo64 > (int64_t)len ? len : (uint32_t)t_lo64);
-    const uint32_t end_rel = (uint32_t)(full_end - (int64_t)c_lo);
-    pos = c_hi;
-
-    if (base_slot != s) { flush(acc_out, base_slot, base, lane); base = make_float2(0.f, 0.f); }
-    uint32_t ph = (a.phase0 + (c_lo + (uint32_t)lane) * a.inc) & 0x7fffu;
-    float2 H[8], R[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { H[u] = sH[(ph + u * inc32) & 255u]; R[u] = make_float2(0.f, 0.f); }
-    float2 sent = make_float2(0.f, 0.f);
-    uint32_t pb = 0; float2 Ab = make_float2(0.f, 0.f);
-    const float2 *__restrict__ urow = a.tab_u;
-    if (t_lo < len) {
-      pb = (a.phase0 + (uint32_t)full_end * a.inc) & 0x7fffu;
-      Ab = sA[pb >> 8];
-      urow = a.tab_u + (size_t)(pb & 255u) * a.taps_len;
-    }
-    const uint32_t roff = c_lo - S_lo + lane;             // segment-relative index of this lane's sample in step 0
-
-    for (uint32_t k = 0; k < len; k += 256, ph = (ph + inc256) & 0x7fffu) {
-      // tiles needed by this batch: up to the one holding its last sample
-      const uint32_t last = min(k + 256u, len) - 1u + (c_lo - S_lo);
-      const uint32_t need = last / kTmaTile + 1;
-      while (landed < need) { mbar_wait(bar_u32 + (landed % kTmaTiles) * 8, (landed / kTmaTiles) & 1u); ++landed; }
-      float2 xv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t j = k + 32 * u + lane;
-        xv[u] = j < len ? ring[(roff + k + 32 * u) & (kTmaRing - 1)] : make_float2(0.f, 0.f);
-      }
-      if (k + 256 <= t_lo) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
-      } else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t js = k + 32 * u;
-          if (js >= len) break;
-          cfma(R[u], sA[((ph + u * inc32) & 0x7fffu) >> 8], xv[u]);
-          if (js + 32 > t_lo) {
-            const uint32_t j = js + lane;
-            if (j >= t_lo && j < len) cfma(sent, cmul(Ab, __ldg(urow + (end_rel - j))), xv[u]);
-          }
-        }
-      }
-      // tiles that lie entirely before the next sample to be read are free: refill them
-      const uint32_t next_rel = min(k + 256u, len) + (c_lo - S_lo);
-      const uint32_t free_upto = next_rel / kTmaTile;       // tiles [0, free_upto) fully consumed
-      __syncwarp();
-      if (lane == 0) {
-        while (issued < n_tiles && issued < free_upto + kTmaTiles) { issue(issued); ++issued; }
-      } else {
-        const uint32_t cap = min(n_tiles, free_upto + (uint32_t)kTmaTiles);
-        if (issued < cap) issued = cap;
-      }
-      __syncwarp();
-    }
-    float2 tot = make_float2(base.x - sent.x, base.y - sent.y);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) cfma(tot, H[u], R[u]);
-    flush(acc_out, s, tot, lane);
-    base = sent; base_slot = s + 1;
-  }
-  flush(acc_out, base_slot, base, lane);
-}
-
 
 // ---- window-pipelined variant (ss <= 512, taps <= 65) ---------------------------------------------
 // A complete interior window is S = ceil(ss/32) steps, fully unrolled.  The warp keeps the S loads of
@@ -682,124 +380,6 @@ static int launch_fold_small(const IqbbFoldArgs &a, cudaStream_t st) {
   return SDRG_OK;
 }
 
-// ---- bandwidth probes (SDRG_FOLD_PROBE=1..3; results are NOT the IQBaseBand output) ---------------
-// Same persistent grid, chunk dealing and staging as iqbb_fold_f32_kernel with the arithmetic reduced
-// to one complex add per sample: what the access pattern itself can reach.  MODE 1: batches of 8 steps
-// (the production schedule); 2: the whole window (<= 16 steps) in one round trip; 3: the first batch of
-// the NEXT chunk is issued before the current chunk's last batch is consumed.
-template <int MODE>
-__global__ void __launch_bounds__(kFoldThreads, MODE == 1 ? 4 : 3) iqbb_fold_probe_kernel(const IqbbFoldArgs a) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t total_warps = gridDim.x * kFoldWarps;
-  const uint32_t wg = warp * gridDim.x + blockIdx.x;
-  const float2 *__restrict__ x = (const float2 *)a.x;
-  float *acc_out = (float *)a.acc_cur;
-  WarpStage stage{(float2 *)dyn_smem + (size_t)warp * kStageRows * kStagePitch, 0u, 0u};
-  const int L1 = (int)a.taps_len - 1;
-  const int win_off = (int)a.first - (int)a.r0;
-  if (MODE == 1) {
-    for (uint32_t id = wg; id < a.n_chunks; id += total_warps) {
-      Chunk c;
-      if (!chunk_of(a, id, win_off, L1, c)) continue;
-      const float2 *__restrict__ xc = x + c.c_lo + lane;
-      float2 R[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) R[u] = make_float2(0.f, 0.f);
-      int k = 0;
-      for (; k + 256 <= c.len; k += 256) {
-        float2 xv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) xv[u] = ld_stream(xc + k + 32 * u);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { R[u].x += xv[u].x; R[u].y += xv[u].y; }
-      }
-      if (k < c.len) {
-        const int rem = c.len - k;
-        float2 xv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { xv[u] = make_float2(0.f, 0.f); if (32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u); }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { R[u].x += xv[u].x; R[u].y += xv[u].y; }
-      }
-      float2 tot = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { tot.x += R[u].x; tot.y += R[u].y; }
-      stage.push(tot, c.s, lane, acc_out);
-    }
-  } else if (MODE == 2) {
-    for (uint32_t id = wg; id < a.n_chunks; id += total_warps) {
-      Chunk c;
-      if (!chunk_of(a, id, win_off, L1, c)) continue;
-      const float2 *__restrict__ xc = x + c.c_lo + lane;
-      float2 tot = make_float2(0.f, 0.f);
-      for (int k = 0; k < c.len; k += 512) {
-        const int rem = c.len - k;
-        float2 xv[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) { xv[u] = make_float2(0.f, 0.f); if (32 * u + lane < rem) xv[u] = ld_stream(xc + k + 32 * u); }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) { tot.x += xv[u].x; tot.y += xv[u].y; }
-      }
-      stage.push(tot, c.s, lane, acc_out);
-    }
-  } else {
-    uint32_t id = wg;
-    Chunk c; bool have = false;
-    for (; id < a.n_chunks; id += total_warps) if (chunk_of(a, id, win_off, L1, c)) { have = true; break; }
-    float2 xa[8];
-    if (have) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { xa[u] = make_float2(0.f, 0.f); if (32 * u + lane < c.len) xa[u] = ld_stream(x + c.c_lo + lane + 32 * u); }
-    }
-    while (have) {
-      const float2 *__restrict__ xc = x + c.c_lo + lane;
-      float2 xb[8];
-      const int rem = c.len - 256;                         // second batch of this chunk (issued first)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { xb[u] = make_float2(0.f, 0.f); if (32 * u + lane < rem) xb[u] = ld_stream(xc + 256 + 32 * u); }
-      float2 tot = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { tot.x += xa[u].x; tot.y += xa[u].y; }
-      Chunk cn; bool haven = false;
-      for (id += total_warps; id < a.n_chunks; id += total_warps) if (chunk_of(a, id, win_off, L1, cn)) { haven = true; break; }
-      if (haven) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { xa[u] = make_float2(0.f, 0.f); if (32 * u + lane < cn.len) xa[u] = ld_stream(x + cn.c_lo + lane + 32 * u); }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { tot.x += xb[u].x; tot.y += xb[u].y; }
-      for (int k = 512; k < c.len; k += 256) {             // longer pieces: plain batches
-        const int r2 = c.len - k;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { xb[u] = make_float2(0.f, 0.f); if (32 * u + lane < r2) xb[u] = ld_stream(xc + k + 32 * u); }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { tot.x += xb[u].x; tot.y += xb[u].y; }
-      }
-      stage.push(tot, c.s, lane, acc_out);
-      c = cn; have = haven;
-    }
-  }
-  stage.drain(lane, acc_out);
-}
-
-template <int MODE>
-static int launch_fold_probe(IqbbFoldArgs a, cudaStream_t st) {
-  const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
-  int sms = 0, per_sm = 0;
-  const int dev = current_device();
-  SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_probe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_probe_kernel<MODE>, kFoldThreads, smem));
-  static const int cap = [] { const char *e = getenv("SDRG_FOLD_PROBE_CTAS"); return e ? atoi(e) : 0; }();
-  if (cap > 0 && cap < per_sm) per_sm = cap;
-  const uint64_t resident = (uint64_t)sms * (per_sm > 0 ? per_sm : 1);
-  const uint64_t want = ((uint64_t)a.n_chunks + kFoldWarps - 1) / kFoldWarps;
-  iqbb_fold_probe_kernel<MODE><<<(unsigned)(want < resident ? want : resident), kFoldThreads, smem, st>>>(a);
-  SDRG_CHECK_LAUNCH("iqbb_fold_probe_kernel");
-  return SDRG_OK;
-}
-
 }  // namespace
 
 // Grids are sized to the machine: 148 SMs x 3 resident CTAs of 8 warps.
@@ -830,9 +410,7 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   static const int small_env = [] { const char *e = getenv("SDRG_FOLD_SMALL"); return e ? atoi(e) : 55; }();   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
   if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) return launch_fold_small(a, st);
   if (!probe && win_env && a.fast && a.ss <= 512 && a.fast_hi >= 1) return launch_fold_win(a, st);
-  if (probe == 1) return launch_fold_probe<1>(a, st);
-  if (probe == 2) return launch_fold_probe<2>(a, st);
-  if (probe == 3) return launch_fold_probe<3>(a, st);
+  if (probe >= 1 && probe <= 3) return launch_fold_probe(probe, a, st);
   static std::atomic<int> resident_dev[kMaxDevices];     // CTAs that fit the device at once: SMs x occupancy
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
   const int dev = current_device();
@@ -851,27 +429,6 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   return SDRG_OK;
 }
 
-static int launch_fold_tma(IqbbFoldArgs a, cudaStream_t st) {
-  static std::atomic<bool> attr_set[kMaxDevices];
-  const size_t smem = (size_t)kFoldWarps * kTmaRing * sizeof(float2);
-  const int dev = current_device();
-  if (!attr_set[dev]) {
-    SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[dev] = true;
-  }
-  // one contiguous 2 KB-aligned segment per warp; ~2 waves of 148 x 3 CTAs
-  const uint64_t target_warps = 148ull * 3 * kFoldWarps * 2;
-  uint64_t seg = (a.n + target_warps - 1) / target_warps;
-  seg = ((seg + kTmaTile - 1) / kTmaTile) * kTmaTile;
-  if (seg < (uint64_t)kTmaTile) seg = kTmaTile;
-  a.seg = (uint32_t)seg;
-  const uint64_t per_block = seg * kFoldWarps;
-  const unsigned grid = (unsigned)((a.n + per_block - 1) / per_block);
-  iqbb_fold_f32_tma_kernel<<<grid, kFoldThreads, smem, st>>>(a);
-  SDRG_CHECK_LAUNCH("iqbb_fold_f32_tma_kernel");
-  return SDRG_OK;
-}
-
 int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st) {
   if (a.n == 0) return SDRG_OK;
   // bulk async copies need 16-byte aligned global addresses; otherwise use the LDG variant
@@ -882,3 +439,4 @@ int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st) {
 }
 
 }  // namespace sdrg
+
