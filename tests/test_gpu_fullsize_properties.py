@@ -91,3 +91,32 @@ def test_c3_full_size_shift_invariance_and_linearity():
     assert rel_rms(yd[d:].cpu().numpy(), y1[:-d].cpu().numpy()) < 1e-5
     z = torch.roll(x, 999) * (0.3 + 0.2j)
     assert rel_rms(run(x + z, 1).cpu().numpy(), (y1 + run(z, 1)).cpu().numpy()) < 1e-5
+
+
+def test_maximum_call_size_crosses_the_2_30_split():
+    """One call of more than 2^30 samples (the library splits launches at 2^30, csrc/api.cu) equals the same
+    stream cut elsewhere: int8 bit-exact, float (window-pipelined kernel) within tolerance; count law."""
+    import torch
+    n = (1 << 30) + 70001
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    x8 = torch.randint(-100, 101, (n, 2), dtype=torch.int8, device="cuda", generator=g)
+    a = IQBaseBand("s8", 100e3, 100e3, 50e3, 15, 50, 0.0); a.config(sample_rate=2.4e6, buffer_size=1 << 20)
+    b = IQBaseBand("s8", 100e3, 100e3, 50e3, 15, 50, 0.0); b.config(sample_rate=2.4e6, buffer_size=1 << 20)
+    ya = a.process(x8)
+    cut = (1 << 29) + 12345
+    yb = torch.cat([b.process(x8[:cut]), b.process(x8[cut:])])
+    torch.cuda.synchronize()
+    assert ya.shape[0] == (n - 1) // 50 and torch.equal(ya, yb)
+    del x8, ya, yb
+    torch.cuda.empty_cache()
+    seg = torch.from_numpy(synth.c2_input(1 << 22)).cuda()
+    xf = seg.repeat(n // seg.shape[0] + 1, 1)[:n].contiguous()
+    cfg = dict(synth.C2)
+    fa, fb = _bb(cfg, 1 << 20), _bb(cfg, 1 << 20)
+    za = fa.process(xf)
+    zb = torch.cat([fb.process(xf[:cut]), fb.process(xf[cut:])])
+    torch.cuda.synchronize()
+    ss = int(cfg["Fs"] / cfg["oFs"])
+    assert za.shape[0] == (n - 1) // ss == zb.shape[0]
+    e = rel_rms(za.cpu().numpy().astype(np.float64).view(np.complex128), zb.cpu().numpy().astype(np.float64).view(np.complex128))
+    assert e < 1e-5, e
