@@ -111,6 +111,7 @@ struct sdrg_iqbb {
   int float_path = 0;                  // 0 auto, 1 direct, 2 folded
   bool fold = false;
   void *d_tab_a = nullptr, *d_tab_u = nullptr;
+  uint32_t *d_work = nullptr;          // work counter of the window-pipelined kernel (0 between calls)
   // stream position
   uint32_t phase0 = 0;
   int parity = 0;
@@ -183,6 +184,8 @@ Advance advance(const sdrg_iqbb *h, uint64_t n) {
 int upload_fold_tables(sdrg_iqbb *h) {
   const IqbbDesign &d = h->d;
   free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
+  if (!h->d_work) SDRG_CUDA(cudaMalloc((void **)&h->d_work, sizeof(uint32_t)));
+  SDRG_CUDA(cudaMemset(h->d_work, 0, sizeof(uint32_t)));
   const size_t L = d.order, ss = d.sub_sample;
   const bool eligible = d.scalar == SDRG_T_F32 && ss >= 2 && ss + 1 >= L;
   if (h->float_path >= 2 && !eligible && d.scalar == SDRG_T_F32)
@@ -361,6 +364,7 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
     fa.n = n; fa.taps_len = (uint32_t)h->d.order; fa.ss = a.ss; fa.r0 = a.r0; fa.first = a.first;
     fa.phase0 = a.nco ? a.phase0 : 0u; fa.inc = a.nco ? a.inc : 0u;
     fa.zero_next = a.zero_next; fa.variant = h->float_path == 3 ? 2u : 0u;
+    fa.work = h->d_work; f.work_reset = h->d_work;
     ProfScope ps(SDRG_KERNEL_IQBB_ACCUM, st);
     rc = launch_iqbb_fold(fa, st);
   } else {
@@ -661,6 +665,7 @@ int sdrg_iqbb_destroy(sdrg_iqbb *h) {
   free_dev(&h->d_hist[0]); free_dev(&h->d_hist[1]);
   free_dev(&h->d_acc[0]); free_dev(&h->d_acc[1]);
   free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
+  if (h->d_work) { cudaFree(h->d_work); h->d_work = nullptr; }
   free_dev(&h->d_in); free_dev(&h->d_out);
   delete h;
   return SDRG_OK;

@@ -71,6 +71,7 @@ __device__ __forceinline__ void iqbb_finalize_block(const IqbbFinalizeArgs &a, c
   const uint32_t j = j0 + tid;
   const bool fm = a.demod == SDRG_DEMOD_FM;
   if (j == 0) {   // carry the open window and (folded float path) the tails already sent past it
+    if (a.work_reset) *a.work_reset = 0u;
     ((typename F::Acc *)a.acc_next)[0] = acc[a.n_out];
     ((typename F::Acc *)a.acc_next)[1] = acc[a.n_out + 1];
     if (fm) {     // carried FM angle: the last sample of this call that contributes

@@ -159,22 +159,38 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
 #pragma unroll
   for (int k = 0; k < 3; ++k) { te[k] = (int)a.ss - 32 * (S - 1 - k) - lane; te_ok[k] = te[k] >= 1 && te[k] <= L1; }
 
-  uint32_t id = wg;
-  if (id == 0) { fold_chunk_general(a, 0u, T, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out); id += T; }
-  if (id <= a.fast_hi) {
+  // Edge chunks (window 0, the clipped last window and the tails behind it) are dealt statically ...
+  if (wg == 0) fold_chunk_general(a, 0u, T, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out);
+  else if (a.fast_hi + wg < a.n_chunks) fold_chunk_general(a, a.fast_hi + wg, T, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out);
+  // ... the complete interior windows 1..fast_hi dynamically, kWorkChunk consecutive windows per grab of a
+  // global counter: a CTA that becomes resident late (another kernel -- e.g. a collective -- holding part of
+  // the SMs) or runs on a slower SM simply takes fewer windows, and ids still advance in address order.
+  // The grab for the chunk after next is issued one chunk ahead and only read when it is needed.
+  const uint32_t kWorkChunk = a.work_chunk;
+  const uint32_t n_work = (a.fast_hi + kWorkChunk - 1) / kWorkChunk;
+  uint32_t grabbed = 0;
+  if (lane == 0) grabbed = atomicAdd(a.work, 1u);
+  const uint32_t c0 = __shfl_sync(kFull, grabbed, 0);
+  if (c0 < n_work) {
+    uint32_t id = 1 + c0 * kWorkChunk, end = min(id + kWorkChunk, a.fast_hi + 1);
+    if (lane == 0) grabbed = atomicAdd(a.work, 1u);               // pending: not read before this chunk's last window
     const float2 *__restrict__ xc = x + ((int)(id * a.ss) + win_off) + lane;
-    const size_t stride = (size_t)T * a.ss;                      // this warp's next window
-    uint32_t ph = a.phase0 + (uint32_t)((int)(id * a.ss) + win_off + lane) * a.inc;   // only bits 0..14 are used
-    uint32_t pb = a.phase0 + (uint32_t)((int)((id + 1) * a.ss) + win_off) * a.inc;
-    const uint32_t dph = (uint32_t)stride * a.inc;
     float2 ring[S];
 #pragma unroll
     for (int i = 0; i + 1 < S; ++i) ring[i] = ld_stream(xc + 32 * i);
     ring[S - 1] = make_float2(0.f, 0.f);
     if (last_ok) ring[S - 1] = ld_stream(xc + 32 * (S - 1));
     for (;;) {
-      const bool more = id + T <= a.fast_hi;
-      const float2 *__restrict__ xn = xc + stride;
+      uint32_t nid = id + 1;
+      bool more = nid < end, switched = false;
+      if (!more) {
+        const uint32_t cn = __shfl_sync(kFull, grabbed, 0);
+        if (cn < n_work) { nid = 1 + cn * kWorkChunk; more = true; switched = true; }
+      }
+      const int c_lo = (int)(id * a.ss) + win_off;
+      const float2 *__restrict__ xn = x + ((int)(nid * a.ss) + win_off) + lane;
+      const uint32_t ph = a.phase0 + (uint32_t)(c_lo + lane) * a.inc;      // only bits 0..14 are used
+      const uint32_t pb = a.phase0 + (uint32_t)(c_lo + (int)a.ss) * a.inc;
       // Tails owed to the next window: the last L-1 samples of the window sit in the last (up to three)
       // ring steps already, so only their weights U(r_b, e), e = ss - 32 i - lane, are fetched (issued
       // now, used ~a window later).  e and its validity are per-lane constants of the launch.
@@ -210,12 +226,14 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
       }
       stage.push(tot, id, lane, acc_out);
       if (L1 > 0 && !(P & 1)) stage.push(sent, id + 1, lane, acc_out);
-      id += T;
       if (!more) break;
-      xc = xn; ph += dph; pb += dph;
+      if (switched) {
+        end = min(nid + kWorkChunk, a.fast_hi + 1);
+        if (lane == 0) grabbed = atomicAdd(a.work, 1u);
+      }
+      id = nid;
     }
   }
-  for (; id < a.n_chunks; id += T) fold_chunk_general(a, id, T, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out);
   stage.drain(lane, acc_out);
 }
 
@@ -406,6 +424,8 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
     a.fast_hi = hi >= 1 ? (uint32_t)hi : 0u;
   }
   static const int win_env = [] { const char *e = getenv("SDRG_FOLD_WIN"); return e ? atoi(e) : 1; }();
+  static const int chunk_env = [] { const char *e = getenv("SDRG_FOLD_WORK_CHUNK"); return e ? atoi(e) : 16; }();
+  a.work_chunk = (uint32_t)(chunk_env > 0 ? chunk_env : 16);
   static const int probe = [] { const char *e = getenv("SDRG_FOLD_PROBE"); return e ? atoi(e) : 0; }();
   static const int small_env = [] { const char *e = getenv("SDRG_FOLD_SMALL"); return e ? atoi(e) : 55; }();   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
   if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) return launch_fold_small(a, st);

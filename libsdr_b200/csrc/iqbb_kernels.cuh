@@ -62,10 +62,13 @@ struct IqbbFoldArgs {
   uint32_t      fast_rs;    // 32-sample steps of the ragged batch (0..8)
   uint32_t      fast_pl;    // lanes of its last step (1..32)
   uint32_t      fast_hi;    // chunk ids 1..fast_hi are complete interior windows (0 = none)
+  uint32_t     *work;       // window-pipelined kernel: work counter (0 at launch; the finalize kernel resets it)
+  uint32_t      work_chunk; // consecutive windows per grab
 };
 
 // finalize (+ optional demodulation) of the completed windows of one call
 struct IqbbFinalizeArgs {
+  uint32_t   *work_reset; // accumulate kernel's work counter, set back to 0 here (may be null)
   const void *acc_cur;    // n_out completed slots followed by the open one
   void       *acc_next;   // slots 0 and 1 receive the carry (open window, and the one after it)
   void       *bb_out;     // complex Scalar[n_out] or null
