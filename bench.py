@@ -351,12 +351,13 @@ def main():
     prof_every = int(os.environ.get("SDRG_BENCH_PROFILE_EVERY", "8"))
     prof_live = [False]
     prof_k0 = [0]
+    prof_off = [0]                # offset inside each group of prof_every steps (away from the step that overlaps a gather launch)
 
     def step_dev():
         k = counter[0]
         counter[0] += 1
         if prof_live[0]:
-            _lib.profile_enable((k - prof_k0[0]) % prof_every == 0)
+            _lib.profile_enable((k - prof_k0[0]) % prof_every == prof_off[0])
         ring, slot = (k // G) & 1, k % G
         if slot == 0 and pending[ring] is not None:
             pending[ring].wait()                    # the gather that last read this ring has finished
@@ -394,6 +395,7 @@ def main():
     _lib.profile_read(_lib.KERNEL_IQBB_ACCUM); _lib.profile_read(_lib.KERNEL_IQBB_FINALIZE)
     prof_live[0] = True
     prof_k0[0] = counter[0]
+    prof_off[0] = min(3, prof_every - 1) if K >= 4 else 0
     l0 = _lib.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -469,7 +471,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "iqbb accumulate (FIR->NCO->window sums), float",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,
-                             "kernel_timing": "CUDA events on the launching stream around the kernel, every %d-th step of the timed region" % prof_every,
+                             "kernel_timing": "CUDA events on the launching stream around the kernel, every %d-th step of the timed region (offset %d)" % (prof_every, prof_off[0]),
                              "peak_note": "the measured peak is a copy (read + write) figure; this kernel is a pure read stream, "
                                           "which HBM3e serves slightly faster, so frac can exceed 1",
                              "kernel_ms": k_ms, "kernel_launches": int(acc_n),
