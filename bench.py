@@ -475,7 +475,7 @@ def main():
                              "peak_note": "the measured peak is a copy (read + write) figure; this kernel is a pure read stream, "
                                           "which HBM3e serves slightly faster, so frac can exceed 1",
                              "kernel_ms": k_ms, "kernel_launches": int(acc_n),
-                             "kernel_share_of_step": (acc_ms / ms) if ms > 0 else None,
+                             "kernel_share_of_step": (k_ms / (ms / K)) if ms > 0 and k_ms else None,
                              "finalize_ms": fin_ms / max(fin_n, 1)},
                 "clocks": clocks, "secondary": secondary}
         if world == 1 and not args.no_cpu_baseline:
