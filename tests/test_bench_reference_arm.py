@@ -22,3 +22,27 @@ def test_reference_arm_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_bench_json_line_contract():
+    """The headline arm on one GPU: one JSON line with the keys the driver reads."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "3", "--no-secondary",
+                        "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert k in d, k
+    assert d["steps"] == 4 and d["n_gpus"] == 1 and d["gpu_launches"] == 8 and d["dtype"] == "f32"
+    ro = d["roofline"]
+    assert ro["bound"] == "hbm" and ro["unit"] == "GB/s" and ro["kernel_launches"] >= 1
+    assert abs(ro["frac"] - ro["achieved"] / ro["peak"]) < 1e-9 and 0.5 < ro["frac"] < 1.1
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == d["config"]["samples_per_step_per_gpu"] * 8 and e["d2h_bytes_per_step"] > 0
+    assert 0 < e["value"] < d["value"]
