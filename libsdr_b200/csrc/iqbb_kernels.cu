@@ -121,6 +121,7 @@ __device__ __forceinline__ void window_sums_int(const IqbbAccumArgs &a, const in
     for (uint32_t s = slot_lo + tid; s <= slot_hi; s += kT) {
       const int lo = max((int)(g.begin(s) - tile_base), 0), hi = min((int)(g.end(s) - tile_base), t_hi);
       uint32_t sr = 0, si = 0;
+#pragma unroll 4
       for (int o = lo; o < hi; ++o) {
         const int2 z = zs[(o & (kR - 1)) * kZRow + (o >> 3)];
         sr += (uint32_t)z.x; si += (uint32_t)z.y;
