@@ -310,6 +310,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    if args.gpus > 1 and world == 1:
+        sys.stderr.write("bench.py: --gpus %d without torch.distributed.run (WORLD_SIZE unset): measuring ONE GPU, n_gpus=1 in the line\n" % args.gpus)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
