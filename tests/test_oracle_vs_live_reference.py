@@ -1,0 +1,74 @@
+"""Pins the oracle against the REFERENCE ITSELF on random node parameters: oracle/_ref/ref_harness is the
+unmodified libsdr classes compiled by oracle/Makefile (a prebuilt binary -- nothing under /root/reference is
+read at run time).  Complements the committed goldens (tests/golden) with configurations nobody hand-picked.
+CPU only; skipped when the harness was never built."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle as orc
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+pytestmark = pytest.mark.skipif(not os.path.exists(HARNESS), reason="oracle/_ref/ref_harness not built")
+
+
+def _params(g):
+    Fs = float(g.choice([48e3, 1e6, 2.4e6, 20e6, 100e6]))
+    order = int(g.integers(1, 41))
+    ss = int(g.choice([1, 2, 3, 7, 8, 31, 32, 50, 64, 65, 125, 300]))
+    Fc = float(g.choice([0.0, 1.0, -1.0]) * g.uniform(0, 0.45) * Fs)
+    Ff = Fc if g.random() < 0.5 else float(g.uniform(-0.4, 0.4) * Fs)
+    width = float(g.uniform(0.001, 0.4) * Fs)
+    return Fs, Fc, Ff, width, order, ss
+
+
+@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("scalar", ["s16", "s8"])
+def test_iqbaseband_and_demods_vs_live_reference(scalar, seed, tmp_path):
+    g = np.random.default_rng(31000 + 100 * (scalar == "s8") + seed)
+    Fs, Fc, Ff, width, order, ss = _params(g)
+    oFs = 0.0 if seed % 2 else Fs / ss                  # both ways of choosing the sub-sampling (baseband.hh:156-160)
+    setcf = seed % 3 == 0
+    dt = np.int16 if scalar == "s16" else np.int8
+    amp = np.iinfo(dt).max if seed % 4 == 0 else np.iinfo(dt).max // 8      # full scale: wrap regime
+    n, bs = 12000, 4096
+    x = g.integers(-amp, amp + 1, size=(n, 2)).astype(dt)
+    inp = tmp_path / "x.bin"; x.tofile(inp)
+    pre = str(tmp_path / "out")
+    subprocess.run([HARNESS, "bb", scalar, str(inp), str(bs), repr(Fs), repr(Fc), repr(Ff), repr(width), str(order), str(ss),
+                    repr(oFs), str(int(setcf)), pre], check=True)
+    sc = orc.S16 if scalar == "s16" else orc.S8
+    o = orc.IQBaseBand(sc, Fc, Ff, width, order, ss, oFs)
+    if setcf:
+        o.set_center_frequency(Fc); o.set_filter_frequency(Ff)
+    o.config(Fs, bs)
+    ofm = orc.FMDemod(sc)
+    bb, fm, am, usb, counts = [], [], [], [], []
+    for k in range(0, n, bs):
+        y = o.process(x[k:k + bs]); counts.append(y.shape[0])
+        if y.shape[0]:
+            bb.append(y); fm.append(ofm.process(y, inplace=True)); am.append(orc.amdemod(y, sc)); usb.append(orc.usbdemod(y, sc))
+    np.testing.assert_array_equal(np.array(counts, dtype=np.uint32), np.fromfile(pre + ".counts", dtype=np.uint32))
+    if bb:
+        np.testing.assert_array_equal(np.concatenate(bb), np.fromfile(pre + ".bb", dtype=dt).reshape(-1, 2))
+        np.testing.assert_array_equal(np.concatenate(fm), np.fromfile(pre + ".fm", dtype=np.int16))
+        np.testing.assert_array_equal(np.concatenate(am), np.fromfile(pre + ".am", dtype=dt))
+        np.testing.assert_array_equal(np.concatenate(usb), np.fromfile(pre + ".usb", dtype=dt))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_real_baseband_vs_live_reference(seed, tmp_path):
+    g = np.random.default_rng(32000 + seed)
+    Fs, Fc, Ff, width, order, ss = _params(g)
+    n, bs = 9000, 2048
+    x = g.integers(-32768, 32768, size=n).astype(np.int16)
+    inp = tmp_path / "x.bin"; x.tofile(inp)
+    pre = str(tmp_path / "out")
+    subprocess.run([HARNESS, "rbb", str(inp), str(bs), repr(Fs), repr(Fc), repr(Ff), repr(width), str(order), str(ss), pre], check=True)
+    o = orc.BaseBand(Fc, Ff, width, order, ss); o.config(Fs, bs)
+    outs = [o.process(x[k:k + bs]) for k in range(0, n, bs)]
+    np.testing.assert_array_equal(np.array([y.shape[0] for y in outs], dtype=np.uint32), np.fromfile(pre + ".counts", dtype=np.uint32))
+    np.testing.assert_array_equal(np.concatenate(outs), np.fromfile(pre + ".bb", dtype=np.int16).reshape(-1, 2))
