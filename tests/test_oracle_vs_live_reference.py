@@ -72,3 +72,43 @@ def test_real_baseband_vs_live_reference(seed, tmp_path):
     outs = [o.process(x[k:k + bs]) for k in range(0, n, bs)]
     np.testing.assert_array_equal(np.array([y.shape[0] for y in outs], dtype=np.uint32), np.fromfile(pre + ".counts", dtype=np.uint32))
     np.testing.assert_array_equal(np.concatenate(outs), np.fromfile(pre + ".bb", dtype=np.int16).reshape(-1, 2))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ola_filter_vs_live_reference(seed, tmp_path):
+    """FilterSink + FilterSource of the reference (with the double-precision FFT stand-in) on random bands."""
+    g = np.random.default_rng(33000 + seed)
+    block = int(g.choice([16, 64, 128, 512, 1024]))
+    Fs = float(g.choice([1e6, 20e6]))
+    f1, f2 = sorted(g.uniform(-0.45, 0.45, size=2) * Fs)
+    nblk = 5
+    x = (g.standard_normal(block * nblk) + 1j * g.standard_normal(block * nblk)).astype(np.complex64)
+    inp = tmp_path / "x.bin"; x.tofile(inp)
+    pre = str(tmp_path / "out")
+    subprocess.run([HARNESS, "ola", str(inp), str(block), repr(Fs), repr(float(f1)), repr(float(f2)), pre], check=True)
+    f = orc.FilterOLA(block, float(f1), float(f2), Fs)
+    np.testing.assert_array_equal(orc.filter_taps(block, float(f1), float(f2), Fs), np.fromfile(pre + ".taps", dtype=np.complex64))
+    np.testing.assert_array_equal(f.kern, np.fromfile(pre + ".kern", dtype=np.complex64))
+    np.testing.assert_array_equal(f.process(x), np.fromfile(pre + ".out", dtype=np.complex64))
+
+
+@pytest.mark.parametrize("fmt,dt", [("cu8", np.uint8), ("cs8", np.int8)])
+def test_autocast_vs_live_reference(fmt, dt, tmp_path):
+    g = np.random.default_rng(34000 + (fmt == "cs8"))
+    x = g.integers(np.iinfo(dt).min, np.iinfo(dt).max + 1, size=(7001, 2)).astype(dt)
+    inp = tmp_path / "x.bin"; x.tofile(inp)
+    pre = str(tmp_path / "out")
+    subprocess.run([HARNESS, "cast", fmt, str(inp), "1000", pre], check=True)
+    np.testing.assert_array_equal(orc.autocast_cs16(x), np.fromfile(pre + ".cs16", dtype=np.int16).reshape(-1, 2))
+
+
+@pytest.mark.parametrize("Fs", [8000.0, 22050.0, 48000.0, 96000.0, 250e3])
+def test_fmdeemph_vs_live_reference(Fs, tmp_path):
+    g = np.random.default_rng(int(Fs))
+    x = g.integers(-32768, 32768, size=5003).astype(np.int16)
+    inp = tmp_path / "x.bin"; x.tofile(inp)
+    pre = str(tmp_path / "out")
+    subprocess.run([HARNESS, "deemph", str(inp), "777", repr(Fs), pre], check=True)
+    d = orc.FMDeemph(Fs)
+    out = np.concatenate([d.process(x[o:o + 777]) for o in range(0, x.shape[0], 777)])
+    np.testing.assert_array_equal(out, np.fromfile(pre + ".out", dtype=np.int16))
