@@ -112,3 +112,31 @@ def test_fmdeemph_vs_live_reference(Fs, tmp_path):
     d = orc.FMDeemph(Fs)
     out = np.concatenate([d.process(x[o:o + 777]) for o in range(0, x.shape[0], 777)])
     np.testing.assert_array_equal(out, np.fromfile(pre + ".out", dtype=np.int16))
+
+
+@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("scalar", ["s16", "s8"])
+def test_product_host_design_vs_live_reference(scalar, seed, tmp_path):
+    """The product's config-time design (csrc/design.cc through sdrg_iqbb_design, no GPU needed) reproduces the
+    reference's own taps, LUT, increment and sub-sampling on random parameters."""
+    from libsdr_b200.nodes import IQBaseBand
+    g = np.random.default_rng(35000 + 100 * (scalar == "s8") + seed)
+    Fs, Fc, Ff, width, order, ss = _params(g)
+    oFs = 0.0 if seed % 2 else Fs / ss
+    dt = np.int16 if scalar == "s16" else np.int8
+    x = np.zeros((64, 2), dtype=dt)
+    inp = tmp_path / "x.bin"; x.tofile(inp)
+    pre = str(tmp_path / "out")
+    subprocess.run([HARNESS, "bb", scalar, str(inp), "64", repr(Fs), repr(Fc), repr(Ff), repr(width), str(order), str(ss),
+                    repr(oFs), "0", pre], check=True)
+    raw = np.fromfile(pre + ".params", dtype=np.uint8)
+    hdr = raw[:32].view(np.int64); L = int(hdr[0])
+    ref_kernel = raw[32:32 + 8 * L].view(np.int32).reshape(L, 2)
+    ref_lut = raw[32 + 8 * L:32 + 8 * L + 8 * 128].view(np.int32).reshape(128, 2)
+    bb = IQBaseBand(scalar, Fc, Ff, width, order, ss, oFs)
+    bb.design_only(sample_rate=Fs, buffer_size=64)
+    inf = bb.info()
+    assert (inf.order, inf.sub_sample, inf.lut_inc, inf.negative_shift) == (L, int(hdr[1]), int(hdr[2]), int(hdr[3]))
+    k, lut = bb.design()
+    np.testing.assert_array_equal(k, ref_kernel)
+    np.testing.assert_array_equal(lut, ref_lut)
