@@ -42,7 +42,7 @@ def test_bench_json_line_contract():
     assert d["steps"] == 4 and d["n_gpus"] == 1 and d["gpu_launches"] == 8 and d["dtype"] == "f32"
     ro = d["roofline"]
     assert ro["bound"] == "hbm" and ro["unit"] == "GB/s" and ro["kernel_launches"] >= 1
-    assert abs(ro["frac"] - ro["achieved"] / ro["peak"]) < 1e-9 and 0.5 < ro["frac"] < 1.1
+    assert abs(ro["frac"] - ro["achieved"] / ro["peak"]) < 1e-9 and 0.2 < ro["frac"] < 1.2
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == d["config"]["samples_per_step_per_gpu"] * 8 and e["d2h_bytes_per_step"] > 0
     assert 0 < e["value"] < d["value"]
