@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDRG_ABI_VERSION 1
+#define SDRG_ABI_VERSION 2
 
 enum {
   SDRG_OK = 0,
@@ -242,6 +242,53 @@ int sdrg_bank_process(sdrg_bank *h, const void *in, size_t buffer_size, size_t n
                       void *usb, size_t out_stride, size_t *n_out);
 int sdrg_bank_process_dev(sdrg_bank *h, const void *d_in, size_t buffer_size, size_t n_buffers, void *d_bb, void *d_fm,
                           void *d_am, void *d_usb, size_t out_stride, size_t *n_out, void *stream);
+
+/* ---- multi-GPU -----------------------------------------------------------------------
+ * The reference has no parallelism (its only thread is the Queue's, src/queue.cc:57-60); the path shards
+ * over independent channels / streams and only demodulated outputs cross GPUs.  Both mechanisms below use
+ * plain peer memory: output rows are written by the producing GPU's finalize kernel (or a copy engine)
+ * directly into the consumer GPU's HBM over NVLink, so no collective kernel competes for SMs.
+ *
+ * (1) One process, G devices: a channel bank whose channels are sharded by contiguous ranges over
+ *     `devices` (shard g owns channels [g*C/G, (g+1)*C/G), the first C%G shards one more).  Same
+ *     semantics and bit-identical results as sdrg_bank_* with all channels on one device.
+ *     _process:     host pointers; every device uploads the input and returns its rows; blocking.
+ *     _process_dev: input and output arrays live on devices[0]; `stream` is a stream of devices[0]; the
+ *                   input is broadcast with copy-engine peer copies, shards with peer access store their
+ *                   rows straight into the output arrays (others stage + peer copy); asynchronous, `stream`
+ *                   is ordered behind all shards on return. */
+typedef struct sdrg_bank_sharded sdrg_bank_sharded;
+int sdrg_bank_sharded_create(int scalar, size_t n_channels, const double *Fc, const double *Ff, double width, size_t order,
+                             size_t sub_sample, double oFs, const int *devices, size_t n_devices, sdrg_bank_sharded **h);
+int sdrg_bank_sharded_destroy(sdrg_bank_sharded *h);
+int sdrg_bank_sharded_configure(sdrg_bank_sharded *h, const sdrg_config *src, sdrg_config *out);
+int sdrg_bank_sharded_info(const sdrg_bank_sharded *h, size_t *channels, size_t *n_shards, size_t shard, int *device,
+                           size_t *first_channel, size_t *n_shard_channels, int *direct_peer_stores);
+int sdrg_bank_sharded_outputs_for(const sdrg_bank_sharded *h, size_t n_in, size_t *n_out);
+int sdrg_bank_sharded_process(sdrg_bank_sharded *h, const void *in, size_t buffer_size, size_t n_buffers, void *bb, void *fm,
+                              void *am, void *usb, size_t out_stride, size_t *n_out);
+int sdrg_bank_sharded_process_dev(sdrg_bank_sharded *h, const void *d_in, size_t buffer_size, size_t n_buffers, void *d_bb,
+                                  void *d_fm, void *d_am, void *d_usb, size_t out_stride, size_t *n_out, void *stream);
+
+/* (2) One process per GPU: peer windows.  The consumer creates a window in its HBM and ships the 64-byte
+ *     handle to the producers (any host channel); a producer opens it and uses addresses inside it as
+ *     output pointers of the *_process_dev calls.  sdrg_peer_signal() publishes a 64-bit progress value
+ *     into a slot (stream-ordered after everything enqueued before it, system-scope release);
+ *     sdrg_peer_wait() holds `stream` until all n_slots consecutive slots are >= value (or timeout_ms
+ *     passed: sdrg_peer_wait_timed_out() then reports 1 once; 0 = 10 s).  Windows start zeroed. */
+#define SDRG_IPC_HANDLE_BYTES 64
+int sdrg_peer_window_create(size_t bytes, void **d_ptr, void *ipc_handle);
+int sdrg_peer_window_open(const void *ipc_handle, void **d_ptr);
+int sdrg_peer_window_close(void *d_ptr);
+int sdrg_peer_window_destroy(void *d_ptr);
+int sdrg_peer_signal(void *d_slot, uint64_t value, void *stream);
+int sdrg_peer_wait(const void *d_slots, size_t n_slots, uint64_t value, unsigned timeout_ms, void *stream);
+int sdrg_peer_wait_timed_out(int *timed_out);
+int sdrg_memcpy_d2d_async(void *d_dst, const void *d_src, size_t bytes, void *stream);   /* same or peer device */
+/* Pinned host memory for feeding `device`: bound to the NUMA node the GPU hangs off (sysfs numa_node; *numa_node
+ * receives it, -1 = unknown / single node, then plain cudaHostAlloc).  For the host-pointer entry points. */
+int sdrg_host_alloc(size_t bytes, int device, void **host_ptr, int *numa_node);
+int sdrg_host_free(void *host_ptr);
 
 /* number of kernels the library has launched so far (all handles, this process) */
 int sdrg_kernel_launch_count(uint64_t *count);

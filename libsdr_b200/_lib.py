@@ -130,6 +130,24 @@ SIGNATURES = {
     "sdrg_bank_outputs_for": [_V, _SZ, _PSZ],
     "sdrg_bank_process": [_V, _V, _SZ, _SZ, _V, _V, _V, _V, _SZ, _PSZ],
     "sdrg_bank_process_dev": [_V, _V, _SZ, _SZ, _V, _V, _V, _V, _SZ, _PSZ, _V],
+    "sdrg_bank_sharded_create": [_I, _SZ, C.POINTER(C.c_double), C.POINTER(C.c_double), _D, _SZ, _SZ, _D,
+                                 C.POINTER(C.c_int), _SZ, _PV],
+    "sdrg_bank_sharded_destroy": [_V],
+    "sdrg_bank_sharded_configure": [_V, _PCFG, _PCFG],
+    "sdrg_bank_sharded_info": [_V, _PSZ, _PSZ, _SZ, C.POINTER(C.c_int), _PSZ, _PSZ, C.POINTER(C.c_int)],
+    "sdrg_bank_sharded_outputs_for": [_V, _SZ, _PSZ],
+    "sdrg_bank_sharded_process": [_V, _V, _SZ, _SZ, _V, _V, _V, _V, _SZ, _PSZ],
+    "sdrg_bank_sharded_process_dev": [_V, _V, _SZ, _SZ, _V, _V, _V, _V, _SZ, _PSZ, _V],
+    "sdrg_peer_window_create": [_SZ, _PV, _V],
+    "sdrg_peer_window_open": [_V, _PV],
+    "sdrg_peer_window_close": [_V],
+    "sdrg_peer_window_destroy": [_V],
+    "sdrg_peer_signal": [_V, C.c_uint64, _V],
+    "sdrg_peer_wait": [_V, _SZ, C.c_uint64, C.c_uint, _V],
+    "sdrg_peer_wait_timed_out": [C.POINTER(C.c_int)],
+    "sdrg_memcpy_d2d_async": [_V, _V, _SZ, _V],
+    "sdrg_host_alloc": [_SZ, _I, _PV, C.POINTER(C.c_int)],
+    "sdrg_host_free": [_V],
     "sdrg_kernel_launch_count": [C.POINTER(C.c_uint64)],
     "sdrg_profile_enable": [_I],
     "sdrg_profile_read": [_I, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],

@@ -139,6 +139,10 @@ struct sdrg_rxchain {
   int parity = 0;
   void *d_in = nullptr, *d_bb = nullptr, *d_audio = nullptr;
   size_t in_cap = 0, bb_cap = 0, audio_cap = 0;
+  // host-pointer entry point: the upload is cut into chunks on two copy streams so that the kernels of
+  // chunk i run while chunk i+1 is still on the wire
+  cudaStream_t copy_st[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> copy_ev;
 };
 
 namespace {
@@ -1120,6 +1124,8 @@ int sdrg_rxchain_destroy(sdrg_rxchain *h) {
   cudaDeviceSynchronize();
   free_dev(&h->d_last[0]); free_dev(&h->d_last[1]);
   free_dev(&h->d_in); free_dev(&h->d_bb); free_dev(&h->d_audio);
+  for (int k = 0; k < 2; ++k) if (h->copy_st[k]) cudaStreamDestroy(h->copy_st[k]);
+  for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
   delete h;
   return SDRG_OK;
 }
@@ -1190,10 +1196,36 @@ int sdrg_rxchain_process(sdrg_rxchain *h, const void *in, size_t buffer_size, si
   if ((rc = grow(&h->d_in, &h->in_cap, n_in * isb))) return rc;
   if ((rc = grow(&h->d_bb, &h->bb_cap, (total + 1) * sb))) return rc;
   if ((rc = grow(&h->d_audio, &h->audio_cap, (total + 1) * (ab ? ab : 1)))) return rc;
-  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, n_in * isb, cudaMemcpyHostToDevice, bb->stream));
+  // Upload in chunks of whole buffers (>= 64 MiB each, at most 16 chunks) on two alternating copy streams;
+  // the compute stream waits for chunk i only, so its kernels overlap the upload of chunk i+1.
+  const size_t buf_bytes = buffer_size * isb;
+  size_t per_chunk = ((size_t)64 << 20) / (buf_bytes ? buf_bytes : 1);
+  if (per_chunk < 1) per_chunk = 1;
+  if ((n_buffers + per_chunk - 1) / per_chunk > 16) per_chunk = (n_buffers + 15) / 16;
+  const size_t n_chunks = (n_buffers + per_chunk - 1) / per_chunk;
+  for (int k = 0; k < 2; ++k)
+    if (!h->copy_st[k]) SDRG_CUDA(cudaStreamCreateWithFlags(&h->copy_st[k], cudaStreamNonBlocking));
+  while (h->copy_ev.size() < n_chunks) {
+    cudaEvent_t e = nullptr;
+    SDRG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->copy_ev.push_back(e);
+  }
   size_t got = 0;
-  rc = sdrg_rxchain_process_dev(h, h->d_in, buffer_size, n_buffers, h->d_bb, h->d_audio, total, &got, counts, bb->stream);
-  if (rc) return rc;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t b0 = c * per_chunk, nb = (n_buffers - b0) < per_chunk ? (n_buffers - b0) : per_chunk;
+    cudaStream_t cs = n_chunks > 1 ? h->copy_st[c & 1] : bb->stream;
+    SDRG_CUDA(cudaMemcpyAsync((char *)h->d_in + b0 * buf_bytes, (const char *)in + b0 * buf_bytes, nb * buf_bytes,
+                              cudaMemcpyHostToDevice, cs));
+    if (n_chunks > 1) {
+      SDRG_CUDA(cudaEventRecord(h->copy_ev[c], cs));
+      SDRG_CUDA(cudaStreamWaitEvent(bb->stream, h->copy_ev[c], 0));
+    }
+    size_t g = 0;
+    rc = sdrg_rxchain_process_dev(h, (char *)h->d_in + b0 * buf_bytes, buffer_size, nb, (char *)h->d_bb + got * sb,
+                                  (char *)h->d_audio + got * ab, total - got, &g, counts ? counts + b0 : nullptr, bb->stream);
+    if (rc) { cudaStreamSynchronize(h->copy_st[0]); cudaStreamSynchronize(h->copy_st[1]); return rc; }
+    got += g;
+  }
   if (got && bb_out) SDRG_CUDA(cudaMemcpyAsync(bb_out, h->d_bb, got * sb, cudaMemcpyDeviceToHost, bb->stream));
   if (got && audio && h->demod != SDRG_DEMOD_NONE)
     SDRG_CUDA(cudaMemcpyAsync(audio, h->d_audio, got * ab, cudaMemcpyDeviceToHost, bb->stream));

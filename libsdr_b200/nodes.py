@@ -301,6 +301,17 @@ class RxChain:
         return bb_out[:got.value], audio_out[:got.value], np.array(counts[:], dtype=np.int64)
 
 
+    def process_into(self, x, buffer_size, bb_ptr, audio_ptr, out_cap):
+        """Device entry point with raw output addresses (e.g. inside a PeerWindow on another GPU):
+        bb_ptr / audio_ptr are integers or None.  Returns the number of outputs."""
+        nb = x.shape[0] // buffer_size
+        got = C.c_size_t(0)
+        _lib.call("sdrg_rxchain_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb,
+                  C.c_void_p(bb_ptr) if bb_ptr else None, C.c_void_p(audio_ptr) if audio_ptr else None,
+                  int(out_cap), C.byref(got), None, _stream_ptr())
+        return got.value
+
+
 class FFTPlan:
     """FFTPlan<float> (src/fftplan_fftw3.hh:79-142): FFTPlan(n, direction) with direction FORWARD/BACKWARD;
     calling the plan transforms `batch` contiguous n-point signals (complex64)."""
@@ -402,6 +413,7 @@ class ChannelBank:
     stream, each with FM/AM/USB demodulators connected out of place (sdrg_bank_*)."""
 
     _in_shape = (-1, 2)
+    _prefix = "sdrg_bank"
 
     def __init__(self, scalar, Fc, Ff, width, order, sub_sample, oFs=0.0):
         self.scalar = scalar_id(scalar)
@@ -426,12 +438,12 @@ class ChannelBank:
         if src_cfg is None:
             src_cfg = Config(_CTYPE[self.scalar] if type is None else type, sample_rate, buffer_size, num_buffers)
         out = Config()
-        _lib.call("sdrg_bank_configure", self._h, C.byref(src_cfg), C.byref(out))
+        _lib.call(self._prefix + "_configure", self._h, C.byref(src_cfg), C.byref(out))
         return out
 
     def outputs_for(self, n_in):
         n = C.c_size_t(0)
-        _lib.call("sdrg_bank_outputs_for", self._h, int(n_in), C.byref(n))
+        _lib.call(self._prefix + "_outputs_for", self._h, int(n_in), C.byref(n))
         return n.value
 
     def channel_info(self, c):
@@ -459,7 +471,7 @@ class ChannelBank:
                     res[k] = torch.zeros(shapes[k][0], dtype=shapes[k][1], device=x.device)
             stride = res[want[0]].shape[1]
             ptr = lambda k: C.c_void_p(res[k].data_ptr()) if k in want else None  # noqa: E731
-            _lib.call("sdrg_bank_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb, ptr("bb"), ptr("fm"),
+            _lib.call(self._prefix + "_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb, ptr("bb"), ptr("fm"),
                       ptr("am"), ptr("usb"), stride, C.byref(got), _stream_ptr())
             return {k: res[k][:, :got.value] for k in want}
         x = np.ascontiguousarray(x, dtype=self.dtype).reshape(-1, 2)
@@ -469,9 +481,66 @@ class ChannelBank:
             if k not in res:
                 res[k] = np.zeros(shapes[k][0], dtype=shapes[k][1])
         ptr = lambda k: _np_ptr(res[k]) if k in want else None  # noqa: E731
-        _lib.call("sdrg_bank_process", self._h, _np_ptr(x), buffer_size, nb, ptr("bb"), ptr("fm"), ptr("am"), ptr("usb"),
+        _lib.call(self._prefix + "_process", self._h, _np_ptr(x), buffer_size, nb, ptr("bb"), ptr("fm"), ptr("am"), ptr("usb"),
                   stride, C.byref(got))
         return {k: res[k][:, :got.value] for k in want}
+
+
+def _bank_process_into(self, x, buffer_size, ptrs, stride):
+    """Device entry point with raw output addresses: ptrs maps "bb"/"fm"/"am"/"usb" to integer device
+    addresses of (channels, stride) arrays (e.g. rows of a PeerWindow on another GPU)."""
+    nb = x.shape[0] // buffer_size
+    got = C.c_size_t(0)
+    p = lambda k: C.c_void_p(ptrs[k]) if ptrs.get(k) else None  # noqa: E731
+    _lib.call(self._prefix + "_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb, p("bb"), p("fm"), p("am"),
+              p("usb"), int(stride), C.byref(got), _stream_ptr())
+    return got.value
+
+
+ChannelBank.process_into = _bank_process_into
+
+
+class ShardedChannelBank(ChannelBank):
+    """The same bank with its channels sharded by contiguous ranges over the GPUs `devices` of THIS process
+    (sdrg_bank_sharded_*): torch tensors in / out live on devices[0]; numpy arrays go through every device's
+    own host<->device copies.  Bit-identical to ChannelBank."""
+
+    _prefix = "sdrg_bank_sharded"
+
+    def __init__(self, scalar, Fc, Ff, width, order, sub_sample, oFs=0.0, devices=(0,)):
+        self.scalar = scalar_id(scalar)
+        self.dtype = _NP[self.scalar]
+        Fc = np.ascontiguousarray(Fc, dtype=np.float64)
+        Ff = Fc if Ff is None else np.ascontiguousarray(Ff, dtype=np.float64)
+        self.channels = Fc.shape[0]
+        self.devices = [int(d) for d in devices]
+        self._h = C.c_void_p()
+        dp = C.POINTER(C.c_double)
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        _lib.call("sdrg_bank_sharded_create", self.scalar, self.channels, Fc.ctypes.data_as(dp), Ff.ctypes.data_as(dp),
+                  float(width), int(order), int(sub_sample), float(oFs), devs, len(self.devices), C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_bank_sharded_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def shards(self):
+        """[(device, first_channel, n_channels, direct_peer_stores)] per shard."""
+        out = []
+        n = C.c_size_t(0)
+        _lib.call("sdrg_bank_sharded_info", self._h, None, C.byref(n), 0, None, None, None, None)
+        for g in range(n.value):
+            dev, lo, cnt, direct = C.c_int(0), C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+            _lib.call("sdrg_bank_sharded_info", self._h, None, None, g, C.byref(dev), C.byref(lo), C.byref(cnt), C.byref(direct))
+            out.append((dev.value, lo.value, cnt.value, bool(direct.value)))
+        return out
+
+    def channel_info(self, c):
+        raise NotImplementedError("per-channel design lives in the shards; build a ChannelBank to inspect it")
 
 
 def autocast_cs16(x):

@@ -25,7 +25,7 @@ def test_header_symbols_exported_and_bound():
     for s in syms:
         assert hasattr(lib, s), "libsdrg.so does not export %s" % s
         assert s in _lib.SIGNATURES, "python binding lacks %s" % s
-    assert lib.sdrg_abi_version() == 1
+    assert lib.sdrg_abi_version() == 2
 
 
 def _make(g):

@@ -91,6 +91,18 @@ def test_full_sdr_fm_chain_with_reference_header_names():
 
 
 @pytest.mark.gpu
+def test_sharded_bank_c_application():
+    """tests/cpp/bank_sharded_test.cc: plain C ABI, 2048 channels over every visible GPU, vs the oracle."""
+    os.makedirs(BUILD, exist_ok=True)
+    obj = os.path.join(BUILD, "sdr_oracle.o")
+    subprocess.run(["gcc", "-O2", "-fwrapv", "-c", os.path.join(ROOT, "oracle", "sdr_oracle.c"), "-o", obj], check=True)
+    exe = compile_cpp("bank_sharded_test", extra=[obj])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bank_sharded_test: ok" in r.stdout
+
+
+@pytest.mark.gpu
 def test_wav_to_wav_real_baseband_fm_chain(tmp_path):
     os.makedirs(BUILD, exist_ok=True)
     obj = os.path.join(BUILD, "sdr_oracle.o")

@@ -104,3 +104,112 @@ def test_bank_rejects_small_subsampling():
     bank = ChannelBank("s16", np.array([1e5]), None, 25e3, 15, 50, 0.0)
     with pytest.raises(ConfigError):
         bank.config(sample_rate=2.4e6, buffer_size=4096)
+
+
+# ---- config 5: 2048 channels ---------------------------------------------------------------------------
+C5_SPOT = (0, 1, 1023, 1024, 1025, 2047, 389, 1707)     # the edges, the centre (inc == 0) and two arbitrary ones
+
+
+def c5_input(n, seed_tail=True):
+    """C5's signal (amplitude 12 per carrier, noise +-8) with the carriers of the spot channels and their
+    neighbours, followed (second half) by full-scale uniform noise so that the wrap regime of the window
+    sums is exercised at 2048 channels as well."""
+    cfg = synth.C5
+    carriers = sorted({(k + d) % cfg["channels"] for k in C5_SPOT for d in (-1, 0, 1)} | set(range(0, 2048, 128)))
+    x = synth.bank_input(n, cfg, carriers=carriers)
+    if seed_tail:
+        g = np.random.Generator(np.random.MT19937(0x5D120055))
+        x[n // 2:] = g.integers(-32768, 32768, size=(n - n // 2, 2)).astype(np.int16)
+    return x
+
+
+def oracle_c5_channel(c, Fc, x, bs):
+    cfg = synth.C5
+    return oracle_channel("s16", Fc[c], Fc[c], cfg["width"], cfg["order"], cfg["sub_sample"], cfg["oFs"], cfg["Fs"], x, bs)
+
+
+def check_c5_outputs(r, Fc, x, bs, channels=C5_SPOT):
+    for c in channels:
+        bb, f, a, u, first = oracle_c5_channel(c, Fc, x, bs)
+        get = lambda k: (r[k][c].cpu().numpy() if hasattr(r[k], "cpu") else r[k][c])  # noqa: E731
+        if "bb" in r:
+            np.testing.assert_array_equal(get("bb"), bb, err_msg="bb ch %d" % c)
+        np.testing.assert_array_equal(get("am"), a, err_msg="am ch %d" % c)
+        mask = np.ones(f.shape[0], dtype=bool); mask[first] = False
+        np.testing.assert_array_equal(get("fm")[mask], f[mask], err_msg="fm ch %d" % c)
+        assert np.all(get("fm")[~mask] == 0)
+
+
+def test_c5_shape_2048_channels():
+    """BASELINE config 5 on ONE GPU: 2048 channels at C5's parameters (15 taps, 100 MS/s -> 48 kHz, amplitude 12),
+    8 spot channels bit-exact against the oracle (base band, FM, AM), two buffers."""
+    import torch
+    cfg = synth.C5
+    Fs, bs = cfg["Fs"], 1 << 17
+    Fc = synth.bank_frequencies(cfg["channels"], Fs)
+    x = c5_input(2 * bs)
+    bank = ChannelBank("s16", Fc, None, cfg["width"], cfg["order"], cfg["sub_sample"], cfg["oFs"])
+    bank.config(sample_rate=Fs, buffer_size=bs)
+    r = bank.process(torch.from_numpy(x).cuda(), bs, want=("bb", "fm", "am"))
+    torch.cuda.synchronize()
+    assert r["fm"].shape == (2048, (2 * bs - 1) // 2083)
+    check_c5_outputs(r, Fc, x, bs)
+
+
+def _visible_devices():
+    import torch
+    return list(range(torch.cuda.device_count()))
+
+
+@pytest.mark.parametrize("layout", ["same_device_x3", "all_devices"])
+def test_sharded_bank_device_pointers(layout):
+    """sdrg_bank_sharded_process_dev: input / outputs on devices[0], shards store their rows there.  On a
+    one-GPU box the three shards share the device (the sharding, row placement and stream joins are the
+    same code); with more GPUs visible every device takes a shard."""
+    import torch
+    from libsdr_b200.nodes import ShardedChannelBank
+    devs = [0, 0, 0] if layout == "same_device_x3" else _visible_devices()
+    if layout == "all_devices" and len(devs) < 2:
+        pytest.skip("one GPU visible")
+    cfg = synth.C5
+    Fs, bs = cfg["Fs"], 1 << 16
+    Fc = synth.bank_frequencies(cfg["channels"], Fs)
+    x = c5_input(3 * bs)
+    bank = ShardedChannelBank("s16", Fc, None, cfg["width"], cfg["order"], cfg["sub_sample"], cfg["oFs"], devices=devs)
+    bank.config(sample_rate=Fs, buffer_size=bs)
+    sh = bank.shards()
+    assert [s[0] for s in sh] == devs and sum(s[2] for s in sh) == 2048 and sh[0][1] == 0
+    if layout == "all_devices":
+        assert all(s[3] for s in sh), "no peer access between the GPUs of this box: %r" % (sh,)
+    xd = torch.from_numpy(x).to("cuda:%d" % devs[0])
+    with torch.cuda.device(devs[0]):
+        r1 = bank.process(xd[:2 * bs], bs, want=("fm", "am"))
+        r1 = {k: v.clone() for k, v in r1.items()}
+        r2 = bank.process(xd[2 * bs:], bs, want=("fm", "am"))       # carried state across calls, per shard
+        torch.cuda.synchronize()
+    r = {k: torch.cat([r1[k], r2[k]], dim=1) for k in r1}
+    check_c5_outputs(r, Fc, x, bs)
+
+
+def test_sharded_bank_host_pointers_equals_single_bank():
+    from libsdr_b200.nodes import ShardedChannelBank
+    devs = _visible_devices()
+    devs = devs if len(devs) > 1 else [0, 0]
+    Fs, bs = 2.4e6, 16384
+    Fc = np.linspace(-1.1e6, 1.1e6, 37)
+    x = synth.iq_int(4 * bs, Fs, [(8000, 103e3, 0.0), (5000, -98e3, 0.5), (3000, 340e3, 1.0)], 64, 9, np.int16)
+    a = ChannelBank("s16", Fc, None, 25e3, 21, 300, 0.0); a.config(sample_rate=Fs, buffer_size=bs)
+    b = ShardedChannelBank("s16", Fc, None, 25e3, 21, 300, 0.0, devices=devs); b.config(sample_rate=Fs, buffer_size=bs)
+    for s, e in ((0, bs), (bs, 4 * bs)):
+        ra, rb = a.process(x[s:e], bs), b.process(x[s:e], bs)
+        for k in ra:
+            np.testing.assert_array_equal(ra[k], rb[k], err_msg=k)
+
+
+def test_sharded_bank_argument_errors():
+    from libsdr_b200.nodes import ShardedChannelBank
+    from libsdr_b200._lib import SDRError
+    with pytest.raises(SDRError):
+        ShardedChannelBank("s16", np.array([1e5, 2e5]), None, 25e3, 15, 300, 0.0, devices=[99])
+    with pytest.raises(SDRError):
+        ShardedChannelBank("s16", np.array([1e5]), None, 25e3, 15, 300, 0.0, devices=[0, 0])
