@@ -52,9 +52,14 @@ typedef struct {
 
 /* ---- runtime ---------------------------------------------------------------------------------- */
 int         sdrg_abi_version(void);
+/* 1 if the library was built with -DSDRG_EXPERIMENTS (environment-variable tuning switches, bandwidth probes and
+ * the TMA staging variant of the float kernel compiled in); 0 for the shipped build, in which no environment
+ * variable can change what is computed.  Returns the flag itself, not a status. */
+int         sdrg_build_has_experiments(void);
 const char *sdrg_last_error(void);
 int         sdrg_device_count(int *count);
 int         sdrg_set_device(int device);          /* device used by handles created afterwards on this thread */
+int         sdrg_get_device(int *device);         /* the calling thread's device (threads start on device 0) */
 int         sdrg_device_synchronize(void);
 
 /* ---- buffer storage (replaces the malloc in RawBuffer::RawBuffer(size_t, BufferOwner*),
@@ -80,6 +85,9 @@ int sdrg_stream_default(void **stream);
 int sdrg_stream_synchronize(void *stream);
 /* device scratch of at least `bytes`, private to the calling thread, valid until its next call */
 int sdrg_scratch(size_t bytes, void **dev_ptr);
+/* a second such scratch, for results that are copied back to foreign (unmanaged) host memory while an input
+ * staged in the first one is still being read */
+int sdrg_scratch_out(size_t bytes, void **dev_ptr);
 int sdrg_memcpy_h2d_async(void *d_dst, const void *h_src, size_t bytes, void *stream);
 int sdrg_memcpy_d2h_async(void *h_dst, const void *d_src, size_t bytes, void *stream);
 
@@ -119,7 +127,8 @@ int sdrg_iqbb_set_input_type(sdrg_iqbb *h, int type);
 /* SDRG_T_F32 only: which accumulate kernel config() selects.  0 = auto (folded when
  * sub_sample >= max(2, order-1), else direct), 1 = direct (sample-by-sample FIR, FMA-bound),
  * 2 = folded (one weight per input sample, HBM-bound; SDRG_ERR_CONFIG at config() if not eligible),
- * 3 = folded with TMA bulk-copy staging through shared memory (experimental; same results).
+ * 3 = folded with TMA bulk-copy staging through shared memory (same results; only in builds with
+ *     SDRG_EXPERIMENTS, otherwise SDRG_ERR_CONFIG).
  * Must be called before config(). */
 int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode);
 

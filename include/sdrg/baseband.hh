@@ -100,13 +100,12 @@ protected:
     if (n_out > out.size()) { RuntimeError err; err << "IQBaseBand: output buffer too small"; throw err; }
     void *d_out = gpu::deviceOutput(out);
     const bool staged = (0 == d_out);           // `out` wraps foreign memory: scratch + copy back
-    void *d_tmp = 0;
-    if (staged && n_out) { gpu::check(sdrg_buffer_alloc(n_out * sizeof(CScalar), &d_tmp)); d_out = gpu::deviceOutput(RawBuffer((char *)d_tmp, 0, 1)); }
+    if (staged && n_out) gpu::check(sdrg_scratch_out(n_out * sizeof(CScalar), &d_out));   // thread-private, reused across calls
     // The finalize kernel writes the outputs only after the accumulate kernel has consumed every
     // input sample (stream order), so `out` may alias `in` on the device as it does on the host.
     gpu::check(sdrg_iqbb_process_dev(_h, d_in, in.size(), d_out, n_out, &n_out, st));
     if (staged) {
-      if (n_out) { gpu::check(sdrg_memcpy_d2h_async(out.data(), d_out, n_out * sizeof(CScalar), st)); gpu::check(sdrg_stream_synchronize(st)); sdrg_buffer_free(d_tmp); }
+      if (n_out) { gpu::check(sdrg_memcpy_d2h_async(out.data(), d_out, n_out * sizeof(CScalar), st)); gpu::check(sdrg_stream_synchronize(st)); }
     } else if (n_out) {
       gpu::publish(out, n_out * sizeof(CScalar), st);
     }

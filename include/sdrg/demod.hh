@@ -28,15 +28,13 @@ protected:
     const void *d_in = gpu::deviceInput(in, st);
     void *d_out = in_place ? const_cast<void *>(d_in) : gpu::deviceOutput(out);
     const bool mirrored = in_place ? (0 != gpu::deviceOutput(in)) : (0 != d_out);
-    void *d_tmp = 0;
-    if (!in_place && !d_out) { gpu::check(sdrg_buffer_alloc(n * sizeof(Out) + 1, &d_tmp)); gpu::check(sdrg_buffer_device_ptr(d_tmp, &d_out)); }
+    if (!in_place && !d_out) gpu::check(sdrg_scratch_out(n * sizeof(Out) + 1, &d_out));   // thread-private, reused across calls
     kernel(d_in, n, d_out, st);
     if (mirrored) {
       gpu::publish(out, n * sizeof(Out), st);
     } else {          // foreign memory: bring the result back now
       gpu::check(sdrg_memcpy_d2h_async(out.data(), d_out, n * sizeof(Out), st));
       gpu::check(sdrg_stream_synchronize(st));
-      if (d_tmp) sdrg_buffer_free(d_tmp);
     }
     this->send(out.head(n), overwrite_downstream);
   }

@@ -70,7 +70,11 @@ public:
     if (_running.load()) return;
     if (_thread.joinable()) _thread.join();
     _running.store(true);
-    _thread = std::thread(&Queue::threadMain, this);
+    // the worker inherits the starting thread's device: nodes created after sdrg_set_device(k) launch on
+    // device k's stream when driven from the Queue thread as well
+    int device = 0;
+    sdrg_get_device(&device);
+    _thread = std::thread(&Queue::threadMain, this, device);
   }
   void stop() { { std::lock_guard<std::mutex> lk(_lock); _running.store(false); } _cond.notify_all(); }
   void wait() { if (_thread.joinable()) _thread.join(); drain(); }
@@ -87,7 +91,8 @@ public:
 protected:
   Queue() : _running(false) {}
   inline void deliver(Message &msg);   // defined in node.hh (needs SinkBase)
-  void threadMain() {
+  void threadMain(int device) {
+    sdrg_set_device(device);      // fails without a GPU: host-only graphs still run
     try { loop(); }
     catch (std::exception &err) {
       LogMessage msg(LOG_ERROR); msg << "Caught exception in thread: " << err.what() << " -> Stop thread.";

@@ -51,9 +51,11 @@ _PSZ, _PV, _PCFG = C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(Confi
 # every symbol include/sdrg.h declares: name -> argtypes (restype is int unless noted)
 SIGNATURES = {
     "sdrg_abi_version": [],
+    "sdrg_build_has_experiments": [],
     "sdrg_last_error": [],
     "sdrg_device_count": [C.POINTER(C.c_int)],
     "sdrg_set_device": [_I],
+    "sdrg_get_device": [C.POINTER(C.c_int)],
     "sdrg_device_synchronize": [],
     "sdrg_buffer_alloc": [_SZ, _PV],
     "sdrg_buffer_free": [_V],
@@ -67,6 +69,7 @@ SIGNATURES = {
     "sdrg_stream_default": [_PV],
     "sdrg_stream_synchronize": [_V],
     "sdrg_scratch": [_SZ, _PV],
+    "sdrg_scratch_out": [_SZ, _PV],
     "sdrg_memcpy_h2d_async": [_V, _V, _SZ, _V],
     "sdrg_memcpy_d2h_async": [_V, _V, _SZ, _V],
     "sdrg_iqbb_create": [_I, _D, _D, _D, _SZ, _SZ, _D, _PV],
@@ -198,6 +201,10 @@ def profile_read(kind):
     ms, n = C.c_double(0), C.c_uint64(0)
     call("sdrg_profile_read", int(kind), C.byref(ms), C.byref(n))
     return ms.value, n.value
+
+
+def has_experiments():
+    return bool(load().sdrg_build_has_experiments())
 
 
 def kernel_launch_count():

@@ -12,10 +12,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsdrg.so")
-SOURCES = ["api.cu", "design.cc", "iqbb_kernels.cu", "iqbb_fold_kernels.cu", "iqbb_fold_experimental.cu", "demod_kernels.cu",
+EXPERIMENTS = os.environ.get("SDRG_EXPERIMENTS", "0") not in ("", "0")     # probes / ablations / tuning switches: not shipped
+SOURCES = ["api.cu", "design.cc", "iqbb_kernels.cu", "iqbb_fold_kernels.cu"] + (["iqbb_fold_experimental.cu"] if EXPERIMENTS else []) + ["demod_kernels.cu",
            "fft_kernels.cu", "fft_api.cu", "bank_kernels.cu", "bank_api.cu", "multi_gpu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-fwrapv,-fno-fast-math", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-O3,-fwrapv,-fno-fast-math", "-shared", "-cudart", "static"] + (["-DSDRG_EXPERIMENTS"] if EXPERIMENTS else [])
 
 
 def sources():
@@ -27,9 +28,20 @@ def _headers():
            [os.path.join(HERE, "..", "include", "sdrg.h")]
 
 
+def _compile_flags(verbose=False):
+    extra = os.environ.get("SDRG_NVCC_EXTRA", "").split()
+    return [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+
+
+def _stamp():
+    return os.path.join(HERE, "..", "build", "obj", "flags.txt")
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
+    if not os.path.exists(_stamp()) or open(_stamp()).read() != " ".join(_compile_flags()):
+        return True                          # built with other flags (e.g. SDRG_EXPERIMENTS)
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(d) > t for d in sources() + _headers())
 
@@ -42,10 +54,9 @@ def build(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     objdir = os.path.join(HERE, "..", "build", "obj")
     os.makedirs(objdir, exist_ok=True)
-    extra = os.environ.get("SDRG_NVCC_EXTRA", "").split()
-    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    flags = _compile_flags(verbose)
     hdr_t = max(os.path.getmtime(h) for h in _headers())
-    stamp = os.path.join(objdir, "flags.txt")
+    stamp = _stamp()
     same_flags = os.path.exists(stamp) and open(stamp).read() == " ".join(flags)
 
     def compile_one(src):

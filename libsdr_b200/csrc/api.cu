@@ -72,6 +72,8 @@ struct ManagedBuffer {
   size_t valid_lo = 0, valid_hi = 0;   // device-valid byte range (what a GPU node produced last)
   bool   host_synced = true;           // that range has been copied back already
   cudaEvent_t ready = nullptr;         // recorded after the producing kernels
+  cudaEvent_t uploaded = nullptr;      // recorded after the last asynchronous host -> device copy out of `host`
+  bool   upload_pending = false;       // ... which the producer must not overtake by refilling `host`
 };
 static std::mutex g_buf_mu;
 static std::map<uintptr_t, ManagedBuffer> g_bufs;   // keyed by host base address
@@ -413,6 +415,13 @@ int config_common(const char *who, int expect_type, const sdrg_config *src, bool
 extern "C" {
 
 int sdrg_abi_version(void) { return SDRG_ABI_VERSION; }
+int sdrg_build_has_experiments(void) {
+#ifdef SDRG_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
 const char *sdrg_last_error(void) { return g_err; }
 
 int sdrg_device_count(int *count) {
@@ -423,6 +432,11 @@ int sdrg_device_count(int *count) {
 int sdrg_set_device(int device) {
   SDRG_CUDA(cudaSetDevice(device));
   g_device = device;
+  return SDRG_OK;
+}
+int sdrg_get_device(int *device) {
+  if (!device) return set_error(SDRG_ERR_ARG, "null argument");
+  *device = g_device;
   return SDRG_OK;
 }
 int sdrg_device_synchronize(void) { SDRG_CUDA(cudaDeviceSynchronize()); return SDRG_OK; }
@@ -465,7 +479,12 @@ int sdrg_buffer_alloc(size_t bytes, void **host_ptr) {
   cudaError_t e = cudaMalloc((void **)&b.dev, bytes ? bytes : 1);
   if (e != cudaSuccess) { cudaFreeHost(b.host); return set_error(SDRG_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
   e = cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming);
-  if (e != cudaSuccess) { cudaFreeHost(b.host); cudaFree(b.dev); return set_error(SDRG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    if (b.ready) cudaEventDestroy(b.ready);
+    cudaFreeHost(b.host); cudaFree(b.dev);
+    return set_error(SDRG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+  }
   std::lock_guard<std::mutex> lk(g_buf_mu);
   g_bufs[(uintptr_t)b.host] = b;
   *host_ptr = b.host;
@@ -484,7 +503,9 @@ int sdrg_buffer_free(void *host_ptr) {
   }
   cudaSetDevice(b.device);
   cudaEventSynchronize(b.ready);
+  if (b.upload_pending) cudaEventSynchronize(b.uploaded);
   cudaEventDestroy(b.ready);
+  cudaEventDestroy(b.uploaded);
   cudaFree(b.dev);
   cudaFreeHost(b.host);
   return SDRG_OK;
@@ -528,10 +549,24 @@ int sdrg_buffer_device_valid(const void *host_ptr, size_t bytes, int *valid) {
   return SDRG_OK;
 }
 
+// The host copy becomes authoritative again, i.e. the buffer goes back to whoever fills it on the host.
+// The reference's process() is synchronous with respect to its input buffer; here an upload out of the pinned
+// host memory may still be in flight (sdrg_buffer_to_device), so it is waited for before the producer may
+// overwrite the bytes.
 int sdrg_buffer_invalidate_device(const void *host_ptr) {
-  std::lock_guard<std::mutex> lk(g_buf_mu);
-  ManagedBuffer *b = find_buffer(host_ptr);
-  if (b) { b->valid_lo = b->valid_hi = 0; b->host_synced = true; }
+  cudaEvent_t wait = nullptr;
+  int device = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_buf_mu);
+    ManagedBuffer *b = find_buffer(host_ptr);
+    if (!b) return SDRG_OK;
+    b->valid_lo = b->valid_hi = 0; b->host_synced = true;
+    if (b->upload_pending) { wait = b->uploaded; device = b->device; b->upload_pending = false; }
+  }
+  if (wait) {
+    SDRG_CUDA(cudaSetDevice(device));
+    SDRG_CUDA(cudaEventSynchronize(wait));
+  }
   return SDRG_OK;
 }
 
@@ -557,6 +592,7 @@ int sdrg_buffer_to_device(const void *host_ptr, size_t bytes, void *stream, void
   if (!dev_ptr) return set_error(SDRG_ERR_ARG, "null argument");
   *dev_ptr = nullptr;
   char *dev = nullptr; bool copy = true; int device = 0;
+  cudaEvent_t uploaded = nullptr;
   {
     std::lock_guard<std::mutex> lk(g_buf_mu);
     ManagedBuffer *b = find_buffer(host_ptr);
@@ -566,10 +602,12 @@ int sdrg_buffer_to_device(const void *host_ptr, size_t bytes, void *stream, void
     dev = b->dev + lo; device = b->device;
     if (b->valid_hi > b->valid_lo && lo >= b->valid_lo && lo + bytes <= b->valid_hi) copy = false;
     else { b->valid_lo = b->valid_hi = 0; b->host_synced = true; }     // the host copy is authoritative
+    if (copy && bytes) { uploaded = b->uploaded; b->upload_pending = true; }
   }
   if (copy && bytes) {
     SDRG_CUDA(cudaSetDevice(device));
     SDRG_CUDA(cudaMemcpyAsync(dev, host_ptr, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    SDRG_CUDA(cudaEventRecord(uploaded, (cudaStream_t)stream));       // waited for in sdrg_buffer_invalidate_device / _free
   }
   *dev_ptr = dev;
   return SDRG_OK;
@@ -595,7 +633,7 @@ int sdrg_stream_synchronize(void *stream) { SDRG_CUDA(cudaStreamSynchronize((cud
 struct ThreadScratch { void *p = nullptr; size_t cap = 0; int device = -1; ~ThreadScratch() { if (p) cudaFree(p); } };
 // slot 0: the caller's scratch (sdrg_scratch); slot 1: the library's own staging of aliased
 // (in-place) results -- kept apart so that an input staged in slot 0 is never overwritten by it
-static thread_local ThreadScratch g_scratch[2];
+static thread_local ThreadScratch g_scratch[3];   // slot 2: staging of outputs for foreign (unmanaged) host memory
 static int scratch_slot(int slot, size_t bytes, void **dev_ptr) {
   ThreadScratch &sc = g_scratch[slot];
   if (sc.device != g_device || sc.cap < bytes) {
@@ -611,6 +649,10 @@ static int scratch_slot(int slot, size_t bytes, void **dev_ptr) {
 int sdrg_scratch(size_t bytes, void **dev_ptr) {
   if (!dev_ptr) return set_error(SDRG_ERR_ARG, "null argument");
   return scratch_slot(0, bytes, dev_ptr);
+}
+int sdrg_scratch_out(size_t bytes, void **dev_ptr) {
+  if (!dev_ptr) return set_error(SDRG_ERR_ARG, "null argument");
+  return scratch_slot(2, bytes, dev_ptr);
 }
 int sdrg_memcpy_h2d_async(void *d_dst, const void *h_src, size_t bytes, void *stream) {
   if (bytes) SDRG_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -768,6 +810,9 @@ int sdrg_iqbb_set_input_type(sdrg_iqbb *h, int type) {
 int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   if (mode < 0 || mode > 3) return set_error(SDRG_ERR_ARG, "IQBaseBand: float path must be 0 (auto), 1 (direct), 2 (folded) or 3 (folded, TMA staging)");
+#ifndef SDRG_EXPERIMENTS
+  if (mode == 3) return set_error(SDRG_ERR_CONFIG, "IQBaseBand: the TMA staging variant exists only in builds made with SDRG_EXPERIMENTS=1");
+#endif
   if (h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: select the float path before config()");
   h->float_path = mode;
   return SDRG_OK;

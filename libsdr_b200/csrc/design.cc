@@ -6,7 +6,8 @@
 //   src/freqshift.hh:26-36   (FreqShiftBase ctor: LUT)
 //   src/freqshift.hh:78-87   (FreqShiftBase::_update_lut_incr)
 // so that truncation to int32 lands on the same integers (checked against the reference's own
-// tables in tests/test_design_parity.py via the golden vectors).
+// tables: tests/test_abi_and_design.py on the golden vectors, tests/test_oracle_vs_live_reference.py on random
+// parameter sets against the live reference harness).
 #include "common.cuh"
 
 #include <cmath>

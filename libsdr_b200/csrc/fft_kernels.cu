@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(1024) filter_ola_kernel(const FilterArgs a) {
 
 int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st) {
   if (batch == 0) return SDRG_OK;
-  static const int r16 = [] { const char *e = getenv("SDRG_FFT_R16"); return e ? atoi(e) : 1; }();
+  static const int r16 = env_int("SDRG_FFT_R16", 1);
   if (r16 && n >= 256 && batch <= 0x7fffffffull) {
     const int tpf = n / 16, fpc = tpf >= 256 ? 1 : 256 / tpf;
     const size_t smem = (size_t)fpc * padded_len(n) * sizeof(float2);
@@ -460,7 +460,7 @@ int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
     attr[dev] = smem;
   }
   int threads = n / 8; if (threads < 32) threads = 32; if (threads > 1024) threads = 1024;
-  static const int r16 = [] { const char *e = getenv("SDRG_FFT_R16"); return e ? atoi(e) : 1; }();
+  static const int r16 = env_int("SDRG_FFT_R16", 1);
   if (n >= 512 && (a.n_filters == 1 || (r16 && a.spec))) {   // in-place stages on a single buffer (n == 16 * threads)
     const size_t smem1 = (size_t)padded_len(n) * sizeof(float2);
     static std::atomic<size_t> attr1[kMaxDevices];

@@ -257,7 +257,8 @@ static int launch_fold_win_s(const IqbbFoldArgs &a, cudaStream_t st) {
 }
 
 static int launch_fold_win(const IqbbFoldArgs &a, cudaStream_t st) {
-  static const int wp = [] { const char *e = getenv("SDRG_FOLD_WINP"); return e ? atoi(e) : 0; }();   // experiments, S = 13 only
+#ifdef SDRG_EXPERIMENTS
+  static const int wp = env_int("SDRG_FOLD_WINP", 0);   // ablations of the S = 13 kernel: WRONG RESULTS, timing only
   if (wp && (a.ss + 31) / 32 == 13) {
     switch (wp) {
       case 1: return launch_fold_win_s<13, 1>(a, st); case 2: return launch_fold_win_s<13, 2>(a, st);
@@ -266,6 +267,7 @@ static int launch_fold_win(const IqbbFoldArgs &a, cudaStream_t st) {
       case 7: return launch_fold_win_s<13, 7>(a, st); case 8: return launch_fold_win_s<13, 8>(a, st); default: break;
     }
   }
+#endif
   switch ((a.ss + 31) / 32) {
     case 1: return launch_fold_win_s<1>(a, st);   case 2: return launch_fold_win_s<2>(a, st);
     case 3: return launch_fold_win_s<3>(a, st);   case 4: return launch_fold_win_s<4>(a, st);
@@ -411,9 +413,9 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   if (n_chunks > 0xffffffffull) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand<float>: too many windows in one call");
   a.n_chunks = (uint32_t)n_chunks;
   a.chunks_per_warp = 0;
-  static const int pf = [] { const char *e = getenv("SDRG_FOLD_PF"); return e ? atoi(e) : 0; }();   // measured: no gain with round-robin chunks
+  static const int pf = env_int("SDRG_FOLD_PF", 0);   // measured: no gain with round-robin chunks
   a.pf_dist = (uint32_t)pf;
-  static const int fast_env = [] { const char *e = getenv("SDRG_FOLD_FAST"); return e ? atoi(e) : 1; }();
+  static const int fast_env = env_int("SDRG_FOLD_FAST", 1);
   a.fast = (fast_env && a.cpw == 1 && a.taps_len <= 65 && a.ss + 1 >= a.taps_len) ? 1u : 0u;
   a.fast_nb = a.ss / 256;
   a.fast_rs = (a.ss % 256 + 31) / 32;
@@ -423,14 +425,20 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
     const int64_t hi = ((int64_t)a.n + (int64_t)a.r0 - (int64_t)a.first) / (int64_t)a.ss - 1;
     a.fast_hi = hi >= 1 ? (uint32_t)hi : 0u;
   }
-  static const int win_env = [] { const char *e = getenv("SDRG_FOLD_WIN"); return e ? atoi(e) : 1; }();
-  static const int chunk_env = [] { const char *e = getenv("SDRG_FOLD_WORK_CHUNK"); return e ? atoi(e) : 16; }();
+  static const int win_env = env_int("SDRG_FOLD_WIN", 1);
+  static const int chunk_env = env_int("SDRG_FOLD_WORK_CHUNK", 16);
   a.work_chunk = (uint32_t)(chunk_env > 0 ? chunk_env : 16);
-  static const int probe = [] { const char *e = getenv("SDRG_FOLD_PROBE"); return e ? atoi(e) : 0; }();
-  static const int small_env = [] { const char *e = getenv("SDRG_FOLD_SMALL"); return e ? atoi(e) : 55; }();   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
+#ifdef SDRG_EXPERIMENTS
+  static const int probe = env_int("SDRG_FOLD_PROBE", 0);   // bandwidth probes: WRONG RESULTS, timing only
+#else
+  constexpr int probe = 0;
+#endif
+  static const int small_env = env_int("SDRG_FOLD_SMALL", 55);   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
   if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) return launch_fold_small(a, st);
   if (!probe && win_env && a.fast && a.ss <= 512 && a.fast_hi >= 1) return launch_fold_win(a, st);
+#ifdef SDRG_EXPERIMENTS
   if (probe >= 1 && probe <= 3) return launch_fold_probe(probe, a, st);
+#endif
   static std::atomic<int> resident_dev[kMaxDevices];     // CTAs that fit the device at once: SMs x occupancy
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
   const int dev = current_device();
@@ -453,9 +461,14 @@ int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st) {
   if (a.n == 0) return SDRG_OK;
   // bulk async copies need 16-byte aligned global addresses; otherwise use the LDG variant
   const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0;
-  static const int env_variant = [] { const char *e = getenv("SDRG_FOLD_VARIANT"); return e ? atoi(e) : 0; }();
-  const int variant = a.variant ? (int)a.variant : env_variant;      // 2 = TMA staging (experimental)
-  return (aligned && variant == 2 && a.ss >= 32) ? launch_fold_tma(a, st) : launch_fold_ldg(a, st);
+#ifdef SDRG_EXPERIMENTS
+  static const int env_variant = env_int("SDRG_FOLD_VARIANT", 0);
+  const int variant = a.variant ? (int)a.variant : env_variant;      // 2 = TMA staging (iqbb_fold_experimental.cu)
+  if (aligned && variant == 2 && a.ss >= 32) return launch_fold_tma(a, st);
+#else
+  (void)aligned;
+#endif
+  return launch_fold_ldg(a, st);
 }
 
 }  // namespace sdrg

@@ -41,6 +41,23 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _dev_in(x, dtype=None, what="input"):
+    """A torch tensor handed to a *_dev entry point: it must live on a GPU, be contiguous (the C ABI sees a raw
+    pointer and a length) and have the element type the node was built for.  Raises ConfigError otherwise --
+    a wrong dtype or a strided view would otherwise be read as garbage or past the end."""
+    import torch
+    if not x.is_cuda:
+        raise ConfigError("%s tensor must live on a CUDA device" % what)
+    if not x.is_contiguous():
+        raise ConfigError("%s tensor must be contiguous (call .contiguous())" % what)
+    if dtype is not None:
+        want = {np.int8: (torch.int8,), np.uint8: (torch.uint8,), np.int16: (torch.int16,), np.float32: (torch.float32, torch.complex64),
+                np.complex64: (torch.complex64, torch.float32)}[np.dtype(dtype).type]
+        if x.dtype not in want:
+            raise ConfigError("%s tensor has dtype %s, the node expects %s" % (what, x.dtype, np.dtype(dtype).name))
+    return C.c_void_p(x.data_ptr())
+
+
 def fm_out_dtype(scalar):
     return np.float32 if scalar == T_F32 else np.int16
 
@@ -135,7 +152,7 @@ class IQBaseBand:
             odt = {np.int8: torch.int8, np.int16: torch.int16, np.float32: torch.float32}[self.dtype]
             out = torch.empty((max(n_out, 1), 2), dtype=odt, device=x.device)
             got = C.c_size_t(0)
-            _lib.call("sdrg_iqbb_process_dev", self._h, C.c_void_p(x.data_ptr()), n_in,
+            _lib.call("sdrg_iqbb_process_dev", self._h, _dev_in(x, getattr(self, "in_dtype", self.dtype)), n_in,
                       C.c_void_p(out.data_ptr()), n_out, C.byref(got), _stream_ptr())
             return out[:got.value]
         x = np.ascontiguousarray(x, dtype=getattr(self, "in_dtype", self.dtype)).reshape(self._in_shape)
@@ -199,7 +216,7 @@ class FMDemod:
             odt = torch.float32 if self.scalar == T_F32 else torch.int16
             if out is None:
                 out = torch.zeros(max(n, 1), dtype=odt, device=x.device)
-            _lib.call("sdrg_fmdemod_process_dev", self._h, C.c_void_p(x.data_ptr()), n,
+            _lib.call("sdrg_fmdemod_process_dev", self._h, _dev_in(x, _NP[self.scalar]), n,
                       C.c_void_p(out.data_ptr()), int(in_place), _stream_ptr())
             return out[:n]
         x = np.ascontiguousarray(x, dtype=_NP[self.scalar]).reshape(-1, 2)
@@ -226,7 +243,7 @@ class _Envelope:
             import torch
             n = x.shape[0]
             out = torch.empty(max(n, 1), dtype=x.dtype, device=x.device)
-            _lib.call("sdrg_%s_process_dev" % self._name, self.scalar, C.c_void_p(x.data_ptr()), n,
+            _lib.call("sdrg_%s_process_dev" % self._name, self.scalar, _dev_in(x, _NP[self.scalar]), n,
                       C.c_void_p(out.data_ptr()), _stream_ptr())
             return out[:n]
         x = np.ascontiguousarray(x, dtype=_NP[self.scalar]).reshape(-1, 2)
@@ -287,8 +304,8 @@ class RxChain:
                 bb_out = torch.empty((max(n_out, 1), 2), dtype=bdt, device=x.device)
             if audio_out is None:
                 audio_out = torch.zeros(max(n_out, 1), dtype=adt, device=x.device)
-            _lib.call("sdrg_rxchain_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb,
-                      C.c_void_p(bb_out.data_ptr()), C.c_void_p(audio_out.data_ptr()), n_out,
+            _lib.call("sdrg_rxchain_process_dev", self._h, _dev_in(x, getattr(self.bb, "in_dtype", self.bb.dtype)), buffer_size, nb,
+                      _dev_in(bb_out, self.bb.dtype, "bb_out"), _dev_in(audio_out, self.audio_dtype(), "audio_out"), n_out,
                       C.byref(got), counts, _stream_ptr())
             return bb_out[:got.value], audio_out[:got.value], np.array(counts[:], dtype=np.int64)
         x = np.ascontiguousarray(x, dtype=getattr(self.bb, "in_dtype", self.bb.dtype)).reshape(-1, 2)
@@ -306,7 +323,7 @@ class RxChain:
         bb_ptr / audio_ptr are integers or None.  Returns the number of outputs."""
         nb = x.shape[0] // buffer_size
         got = C.c_size_t(0)
-        _lib.call("sdrg_rxchain_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb,
+        _lib.call("sdrg_rxchain_process_dev", self._h, _dev_in(x, getattr(self.bb, "in_dtype", self.bb.dtype)), buffer_size, nb,
                   C.c_void_p(bb_ptr) if bb_ptr else None, C.c_void_p(audio_ptr) if audio_ptr else None,
                   int(out_cap), C.byref(got), None, _stream_ptr())
         return got.value
@@ -334,7 +351,7 @@ class FFTPlan:
         if _is_torch(x):
             import torch
             out = torch.empty_like(x)
-            _lib.call("sdrg_fft_exec_dev", self._h, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+            _lib.call("sdrg_fft_exec_dev", self._h, _dev_in(x, np.complex64), C.c_void_p(out.data_ptr()),
                       x.numel() // self.n, _stream_ptr())
             return out
         x = np.ascontiguousarray(x, dtype=np.complex64)
@@ -398,7 +415,7 @@ class FilterNode:
             n_in = x.shape[0]
             n_out = self.outputs_for(n_in)
             out = torch.empty((F, max(n_out, 1)), dtype=torch.complex64, device=x.device)
-            _lib.call("sdrg_filter_process_dev", self._h, C.c_void_p(x.data_ptr()), n_in, C.c_void_p(out.data_ptr()),
+            _lib.call("sdrg_filter_process_dev", self._h, _dev_in(x, np.complex64), n_in, C.c_void_p(out.data_ptr()),
                       max(n_out, 1), C.byref(got), _stream_ptr())
             return out[:, :got.value]
         x = np.ascontiguousarray(x, dtype=np.complex64).reshape(-1)
@@ -471,7 +488,7 @@ class ChannelBank:
                     res[k] = torch.zeros(shapes[k][0], dtype=shapes[k][1], device=x.device)
             stride = res[want[0]].shape[1]
             ptr = lambda k: C.c_void_p(res[k].data_ptr()) if k in want else None  # noqa: E731
-            _lib.call(self._prefix + "_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb, ptr("bb"), ptr("fm"),
+            _lib.call(self._prefix + "_process_dev", self._h, _dev_in(x, self.dtype), buffer_size, nb, ptr("bb"), ptr("fm"),
                       ptr("am"), ptr("usb"), stride, C.byref(got), _stream_ptr())
             return {k: res[k][:, :got.value] for k in want}
         x = np.ascontiguousarray(x, dtype=self.dtype).reshape(-1, 2)
@@ -492,7 +509,7 @@ def _bank_process_into(self, x, buffer_size, ptrs, stride):
     nb = x.shape[0] // buffer_size
     got = C.c_size_t(0)
     p = lambda k: C.c_void_p(ptrs[k]) if ptrs.get(k) else None  # noqa: E731
-    _lib.call(self._prefix + "_process_dev", self._h, C.c_void_p(x.data_ptr()), buffer_size, nb, p("bb"), p("fm"), p("am"),
+    _lib.call(self._prefix + "_process_dev", self._h, _dev_in(x, self.dtype), buffer_size, nb, p("bb"), p("fm"), p("am"),
               p("usb"), int(stride), C.byref(got), _stream_ptr())
     return got.value
 

@@ -108,3 +108,23 @@ def test_product_never_touches_oracle():
                     if re.search(r"oracle[/.]|sdr_oracle|liboracle|import oracle", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_shipped_library_has_no_result_changing_switches():
+    """The default build must not honour any environment variable of its own: no SDRG_* name in the .so (the
+    static CUDA runtime still reads its CUDA_* variables), the probe / ablation / TMA kernels are not linked,
+    and float path 3 is refused."""
+    import subprocess
+    lib = _lib.load()
+    assert lib.sdrg_build_has_experiments() == 0
+    so = _lib.LIB_PATH
+    names = subprocess.run(["strings", so], capture_output=True, text=True, check=True).stdout
+    assert "SDRG_FOLD" not in names and "SDRG_FFT_R16" not in names
+    assert "SDRG_" not in names.replace("SDRG_ERR", "").replace("SDRG_T_", "").replace("SDRG_EXPERIMENTS", "")
+    syms = subprocess.run(["nm", "-C", so], capture_output=True, text=True, check=True).stdout
+    assert "launch_fold_probe" not in syms and "launch_fold_tma" not in syms
+    h = C.c_void_p()
+    _lib.call("sdrg_iqbb_create", _lib.T_F32, 1e5, 1e5, 1e4, 16, 64, 0.0, C.byref(h))
+    with pytest.raises(_lib.ConfigError):
+        _lib.call("sdrg_iqbb_set_float_path", h, 3)
+    lib.sdrg_iqbb_destroy(h)
