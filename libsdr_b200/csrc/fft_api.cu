@@ -57,12 +57,21 @@ std::complex<float> sinc_tap(int i, int N, double Fc, double bw, double Fs) {
   return v;
 }
 
+int upload_tab8k(void **d_tab) {
+  std::vector<float> tab;
+  fft8k_tables(tab);
+  SDRG_CUDA(cudaMalloc(d_tab, tab.size() * sizeof(float)));
+  SDRG_CUDA(cudaMemcpy(*d_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SDRG_OK;
+}
+
 }  // namespace
 
 struct sdrg_fft {
   int device = 0;
   size_t n = 0; int log2n = 0; int inverse = 0;
   void *d_tw = nullptr;
+  void *d_tab8k = nullptr;               // n = 4096 / 8192: tables of fft8k_kernels.cu
   cudaStream_t stream = nullptr;
   void *d_in = nullptr, *d_out = nullptr; size_t cap = 0;
 };
@@ -76,6 +85,7 @@ struct sdrg_filter {
   bool configured = false;
   std::vector<FilterBand> bands;
   void *d_tw = nullptr, *d_kern = nullptr; bool kern_dirty = true;
+  void *d_kperm = nullptr, *d_tab8k = nullptr;         // block 4096: permuted spectra + tables of fft8k_kernels.cu
   void *d_hist[2] = {nullptr, nullptr}; int parity = 0;
   void *d_pend = nullptr; size_t pending = 0;          // re-chunking (BufferNode): < block samples waiting
   void *d_stage = nullptr; size_t stage_cap = 0;
@@ -112,10 +122,20 @@ int upload_kernels(sdrg_filter *h) {
   if (!h->kern_dirty) return SDRG_OK;
   const size_t n2 = 2 * h->block, F = h->bands.size();
   if (h->d_kern) { SDRG_CUDA(cudaDeviceSynchronize()); cudaFree(h->d_kern); h->d_kern = nullptr; }
+  if (h->d_kperm) { cudaFree(h->d_kperm); h->d_kperm = nullptr; }
   if (F) {
     SDRG_CUDA(cudaMalloc(&h->d_kern, F * n2 * 2 * sizeof(float)));
     for (size_t f = 0; f < F; ++f)
       SDRG_CUDA(cudaMemcpy((float *)h->d_kern + f * n2 * 2, h->bands[f].kern.data(), n2 * 2 * sizeof(float), cudaMemcpyHostToDevice));
+    if (n2 == 8192) {
+      std::vector<float> kp(n2 * 2);
+      SDRG_CUDA(cudaMalloc(&h->d_kperm, F * n2 * 2 * sizeof(float)));
+      for (size_t f = 0; f < F; ++f) {
+        fft8k_permute_kernel(h->bands[f].kern.data(), kp.data());
+        SDRG_CUDA(cudaMemcpy((float *)h->d_kperm + f * n2 * 2, kp.data(), n2 * 2 * sizeof(float), cudaMemcpyHostToDevice));
+      }
+      if (!h->d_tab8k) { int rc = upload_tab8k(&h->d_tab8k); if (rc) return rc; }
+    }
   }
   h->kern_dirty = false;
   return SDRG_OK;
@@ -150,7 +170,8 @@ int sdrg_fft_create(size_t n, int direction, sdrg_fft **out) {
   int dev = 0; cudaGetDevice(&dev);
   h->device = dev; h->n = n; h->log2n = ilog2(n); h->inverse = direction ? 1 : 0;
   int rc = upload_twiddles(n, &h->d_tw);
-  if (rc) { delete h; return rc; }
+  if (rc == SDRG_OK && (n == 4096 || n == 8192)) rc = upload_tab8k(&h->d_tab8k);
+  if (rc) { cudaFree(h->d_tw); delete h; return rc; }
   *out = h;
   return SDRG_OK;
 }
@@ -158,13 +179,14 @@ int sdrg_fft_destroy(sdrg_fft *h) {
   if (!h) return SDRG_OK;
   cudaSetDevice(h->device); cudaDeviceSynchronize();
   if (h->stream) cudaStreamDestroy(h->stream);
-  cudaFree(h->d_tw); cudaFree(h->d_in); cudaFree(h->d_out);
+  cudaFree(h->d_tw); cudaFree(h->d_tab8k); cudaFree(h->d_in); cudaFree(h->d_out);
   delete h;
   return SDRG_OK;
 }
 int sdrg_fft_exec_dev(sdrg_fft *h, const void *d_in, void *d_out, size_t batch, void *stream) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   SDRG_CUDA(cudaSetDevice(h->device));
+  if (h->d_tab8k) return launch_fft8k(d_in, d_out, (int)h->n, h->inverse, batch, h->d_tab8k, (cudaStream_t)stream);
   return launch_fft_batch(d_in, d_out, (int)h->n, h->log2n, h->inverse, batch, h->d_tw, (cudaStream_t)stream);
 }
 int sdrg_fft_exec(sdrg_fft *h, const void *in, void *out, size_t batch) {
@@ -203,7 +225,7 @@ int sdrg_filter_destroy(sdrg_filter *h) {
   if (!h) return SDRG_OK;
   cudaSetDevice(h->device); cudaDeviceSynchronize();
   if (h->stream) cudaStreamDestroy(h->stream);
-  cudaFree(h->d_tw); cudaFree(h->d_kern); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
+  cudaFree(h->d_tw); cudaFree(h->d_kern); cudaFree(h->d_kperm); cudaFree(h->d_tab8k); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
   cudaFree(h->d_pend); cudaFree(h->d_stage); cudaFree(h->d_spec); cudaFree(h->d_in); cudaFree(h->d_out);
   delete h;
   return SDRG_OK;
@@ -295,8 +317,9 @@ int sdrg_filter_process_dev(sdrg_filter *h, const void *d_in, size_t n_in, void 
     a.x = src; a.hist_in = h->d_hist[h->parity]; a.hist_out = h->d_hist[h->parity ^ 1];
     a.kern = h->d_kern; a.out = d_out; a.out_stride = out_stride; a.tw = h->d_tw;
     a.block = (int)N; a.log2n = h->log2n; a.n_filters = (int)h->bands.size();
-    a.spec = nullptr;
-    const size_t spec_bytes = nblk * 2 * N * sb;
+    a.spec = nullptr; a.kperm = h->d_kperm; a.tab8k = h->d_tab8k;
+    size_t spec_bytes = nblk * 2 * N * sb;
+    if (a.n_filters > 1 && 2 * N == 8192 && a.kperm) spec_bytes = (size_t)conv8k_grid(nblk) * 8192 * sb;   // one 64 KB line per CTA
     if (a.n_filters > 1 && 2 * N >= 512 && spec_bytes <= ((size_t)2 << 30)) {
       rc = grow_dev(&h->d_spec, &h->spec_cap, spec_bytes);
       if (rc) return rc;

@@ -19,69 +19,12 @@
 // (j div Ns) Ns R + (j mod Ns) + r Ns.  Twiddles come from a table of n-th roots of unity computed
 // in double on the host.  Data ping-pongs between shared-memory buffers; one __syncthreads per stage.
 #include "fft_kernels.cuh"
+#include "fft_device.cuh"
 #include <atomic>
 #include <cstdlib>
 
 namespace sdrg {
 namespace {
-
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// multiply by -i (forward) or +i (inverse)
-template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
-
-template <bool INV> __device__ __forceinline__ void dft2(float2 &a, float2 &b) { const float2 t = a; a = caddf(t, b); b = csubf(t, b); }
-template <bool INV> __device__ __forceinline__ void dft4(float2 *v) {
-  dft2<INV>(v[0], v[2]); dft2<INV>(v[1], v[3]);
-  v[3] = rot90<INV>(v[3]);
-  dft2<INV>(v[0], v[1]); dft2<INV>(v[2], v[3]);
-  const float2 t = v[1]; v[1] = v[2]; v[2] = t;       // bit reversal: outputs 0,2,1,3 -> natural
-}
-template <bool INV> __device__ __forceinline__ void dft8(float2 *v) {
-  const float h = 0.70710678118654752440f;
-  dft2<INV>(v[0], v[4]); dft2<INV>(v[1], v[5]); dft2<INV>(v[2], v[6]); dft2<INV>(v[3], v[7]);
-  // twiddles w8^k on the odd half: 1, (1-i)/sqrt2, -i, (-1-i)/sqrt2   (conjugated for the inverse)
-  v[5] = INV ? make_float2(h * (v[5].x - v[5].y), h * (v[5].x + v[5].y)) : make_float2(h * (v[5].x + v[5].y), h * (v[5].y - v[5].x));
-  v[6] = rot90<INV>(v[6]);
-  v[7] = INV ? make_float2(h * (-v[7].x - v[7].y), h * (v[7].x - v[7].y)) : make_float2(h * (v[7].y - v[7].x), h * (-v[7].x - v[7].y));
-  dft2<INV>(v[0], v[2]); dft2<INV>(v[1], v[3]); dft2<INV>(v[4], v[6]); dft2<INV>(v[5], v[7]);
-  v[3] = rot90<INV>(v[3]); v[7] = rot90<INV>(v[7]);
-  dft2<INV>(v[0], v[1]); dft2<INV>(v[2], v[3]); dft2<INV>(v[4], v[5]); dft2<INV>(v[6], v[7]);
-  // outputs are in bit-reversed order 0,4,2,6,1,5,3,7
-  float2 t;
-  t = v[1]; v[1] = v[4]; v[4] = t;
-  t = v[3]; v[3] = v[6]; v[6] = t;
-}
-
-// 16-point DFT as 4 x 4 (Cooley-Tukey): DFT4 over r1 of v[4 r1 + r0], twiddle w16^(r0 q0), DFT4 over r0;
-// result V[4 q1 + q0] in natural order.
-template <bool INV> __device__ __forceinline__ float2 mulw16(float2 a, const float c, const float sn) {
-  // a * (c - i sn) forward, a * (c + i sn) inverse
-  return INV ? make_float2(a.x * c - a.y * sn, a.y * c + a.x * sn) : make_float2(a.x * c + a.y * sn, a.y * c - a.x * sn);
-}
-template <bool INV> __device__ __forceinline__ void dft16(float2 *v) {
-  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
-  float2 a[4][4];                                   // a[r0][q0]
-#pragma unroll
-  for (int r0 = 0; r0 < 4; ++r0) {
-    float2 t[4] = {v[r0], v[4 + r0], v[8 + r0], v[12 + r0]};
-    dft4<INV>(t);
-#pragma unroll
-    for (int q0 = 0; q0 < 4; ++q0) a[r0][q0] = t[q0];
-  }
-  // w16^(r0 q0): exponents 1,2,3 / 2,4,6 / 3,6,9
-  a[1][1] = mulw16<INV>(a[1][1], c1, s1); a[1][2] = mulw16<INV>(a[1][2], h, h);  a[1][3] = mulw16<INV>(a[1][3], s1, c1);
-  a[2][1] = mulw16<INV>(a[2][1], h, h);   a[2][2] = rot90<INV>(a[2][2]);         a[2][3] = mulw16<INV>(a[2][3], -h, h);
-  a[3][1] = mulw16<INV>(a[3][1], s1, c1); a[3][2] = mulw16<INV>(a[3][2], -h, h); a[3][3] = mulw16<INV>(a[3][3], -c1, -s1);
-#pragma unroll
-  for (int q0 = 0; q0 < 4; ++q0) {
-    float2 t[4] = {a[0][q0], a[1][q0], a[2][q0], a[3][q0]};
-    dft4<INV>(t);
-#pragma unroll
-    for (int q1 = 0; q1 < 4; ++q1) v[4 * q1 + q0] = t[q1];
-  }
-}
 
 // Shared-memory index padding: one spare element after every 16 (= one 128-byte row of 8-byte
 // elements).  Consecutive reads stay conflict free (an aligned half-warp never straddles a pad),
@@ -452,6 +395,7 @@ int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, s
 int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
   if (n_blocks == 0) return SDRG_OK;
   const int n = 2 * a.block;
+  if (n == 8192 && a.n_filters >= 1 && a.kperm && a.tab8k) return launch_conv8k(a, n_blocks, st);
   const size_t smem = (size_t)3 * padded_len(n) * sizeof(float2);
   static std::atomic<size_t> attr[kMaxDevices];
   const int dev = current_device();

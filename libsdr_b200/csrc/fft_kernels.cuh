@@ -18,9 +18,21 @@ struct FilterArgs {
   int         log2n;      // log2(2*block)
   int         n_filters;
   void       *spec;       // multi-filter radix-16 path: spectra of the blocks, n_blocks x 2*block (null: fused 3-buffer kernel)
+  const void *kperm;      // block 4096 only (fft8k_kernels.cu): the spectra in the kernel's digit-reversed order, pre-scaled by 1/8192
+  const void *tab8k;      // ... and its twiddle tables
 };
 
 int launch_fft_batch(const void *in, void *out, int n, int log2n, int inverse, size_t batch, const void *tw, cudaStream_t st);
 int launch_filter_ola(const FilterArgs &a, size_t n_blocks, cudaStream_t st);
+
+// fft8k_kernels.cu: n = 8192 / 4096 transforms and the block-4096 convolution (in-place radix-16 stages, table twiddles)
+}  // namespace sdrg
+#include <vector>
+namespace sdrg {
+void fft8k_tables(std::vector<float> &tab);                           // host: the twiddle tables (interleaved re, im)
+void fft8k_permute_kernel(const float *kern_8192, float *kperm_8192); // host: spectrum -> kernel order, x 1/8192
+int launch_fft8k(const void *in, void *out, int n, int inverse, size_t batch, const void *tab, cudaStream_t st);
+int launch_conv8k(const FilterArgs &a, size_t n_blocks, cudaStream_t st);
+int conv8k_grid(size_t n_blocks);   // CTAs that launch will use: a filter bank needs 64 KB of FilterArgs::spec per CTA
 
 }  // namespace sdrg

@@ -76,8 +76,9 @@ def test_filter_c3_shape_against_oracle_and_time_domain():
     assert rel_rms(y[:8 * c["block"]], td) < TOL
 
 
-def test_filter_bank_shared_forward_fft():
-    block, Fs = 1024, 2.4e6
+@pytest.mark.parametrize("block", [1024, 4096])       # 4096: the in-place radix-16 bank kernel (fft8k_kernels.cu)
+def test_filter_bank_shared_forward_fft(block):
+    Fs = 2.4e6
     x = synth.iq_f32(40 * block, Fs, [(0.5, 150e3, 0.0), (0.3, -400e3, 1.0), (0.2, 900e3, 2.0)], 0.01, 5).view(np.complex64).reshape(-1)
     bands = [(100e3, 200e3), (-500e3, -300e3), (1e6, 800e3), (-1.2e6, 1.2e6)]
     f = FilterNode(block)
