@@ -66,6 +66,8 @@ __device__ __forceinline__ float2 root8k(const float2 wt, const int a) {
   constexpr float s32[16] = {0.000000000e+00f, 1.950903220e-01f, 3.826834324e-01f, 5.555702330e-01f, 7.071067812e-01f, 8.314696123e-01f,
                              9.238795325e-01f, 9.807852804e-01f, 1.0f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f,
                              7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f};
+  if (a == 0) return wt;
+  if (a == 8) return make_float2(wt.y, -wt.x);
   // wt * (c - i s)
   return make_float2(wt.x * c32[a] + wt.y * s32[a], wt.y * c32[a] - wt.x * s32[a]);
 }
@@ -76,13 +78,19 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // Both halves go through a stage together: twice the independent work per thread, and every table twiddle is
 // loaded once for the two butterflies that need it.
 // stage 1: e[a] = u0[256 a + t], o[a] = u1[256 a + t] on entry (thread t = 16 b + c)
+// The CTA barrier that frees the buffers (everybody has finished READING the previous item's last stage) sits between
+// the butterflies and the stores, so the global-load latency and the first DFTs of an item overlap the tail of the
+// previous one.
 template <bool INV>
 __device__ __forceinline__ void dif_stage1(float2 *e, float2 *o, float2 *H0, const float2 *tab, const int t) {
   const int pt = pos3(0, t >> 4, t & 15);
   dft16<INV>(e);
   dft16<INV>(o);
+  __syncthreads();
+  H0[pt] = e[0];
+  H0[pt + kHalfPad] = o[0];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
+  for (int q = 1; q < 16; ++q) {
     const float2 w = tab[kT1 + 256 * q + t];
     H0[pt + pos3(q, 0, 0)] = cmulw<INV>(e[q], w);
     H0[pt + pos3(q, 0, 0) + kHalfPad] = cmulw<INV>(o[q], w);
@@ -98,8 +106,10 @@ __device__ __forceinline__ void dif_stage2(float2 *H0, const float2 *tab, const 
   for (int b = 0; b < 16; ++b) { e[b] = B[pos3(0, b, 0)]; o[b] = B[pos3(0, b, 0) + kHalfPad]; }
   dft16<INV>(e);
   dft16<INV>(o);
+  B[0] = e[0];
+  B[kHalfPad] = o[0];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
+  for (int q = 1; q < 16; ++q) {
     const float2 w = tab[kT2 + 16 * q + c];
     B[pos3(0, q, 0)] = cmulw<INV>(e[q], w);
     B[pos3(0, q, 0) + kHalfPad] = cmulw<INV>(o[q], w);
@@ -108,6 +118,10 @@ __device__ __forceinline__ void dif_stage2(float2 *H0, const float2 *tab, const 
 // stage 3: thread t = qa + 16 qb reads the 16 consecutive positions of 256 qa + 16 qb + c (128-bit loads);
 // on return v[qc] = U[t + 256 qc]
 __device__ __forceinline__ int stage3_pos(const int t) { return pos3(t & 15, t >> 4, 0); }
+// The convolution does not care in which order the bins come out, so its stage 3 uses thread t = 16 qa + qb instead:
+// the 16 positions it reads were all written (stage 2, threads 16 qa + c) by lanes of the SAME warp, and the inverse
+// mirror holds too -- two of the five CTA barriers per block become __syncwarp().  Bins held: qa + 16 qb + 256 qc.
+__device__ __forceinline__ int stage3_pos_conv(const int t) { return pos3(t >> 4, t & 15, 0); }
 __device__ __forceinline__ void load16(float2 *v, const float2 *H, const int p0) {
   const float4 *h4 = (const float4 *)(H + p0);
 #pragma unroll
@@ -170,14 +184,14 @@ __global__ void __launch_bounds__(kT, 2) fft8k_kernel(const float2 *__restrict__
 #pragma unroll
         for (int q = 0; q < 16; ++q) { ya[t + 256 * q] = e[q]; if (second) yb[t + 256 * q] = o[q]; }
       }
-    }
-    __syncthreads();             // stage 3 only read: the next item's stage 1 may overwrite now
+    }                            // (stage 3 only read; the barrier inside the next item's stage 1 orders its stores behind this)
   }
 }
 
 // ---- block-4096 overlap-save convolution, fused ------------------------------------------------------------
 // y[N + j] = IDFT_8192(DFT_8192([prev | cur]) K)[N + j] / 8192 = v0[j] - conj(w_8192^j) v1[j], v_h the 4096-point
-// backward DFTs of the even / odd bins.  K arrives permuted and pre-scaled: kp[(h 16 + qc) 256 + t] = K[2 (t + 256 qc) + h] / 8192.
+// backward DFTs of the even / odd bins.  K arrives permuted and pre-scaled: kp[(h 16 + qc) 256 + t] = K[2 m + h] / 8192,
+// m = (t >> 4) + 16 (t & 15) + 256 qc the bin thread t holds after stage 3.
 // BANK = false: one filter; the last forward stage, the spectrum multiply and the first inverse stage stay in registers.
 // BANK = true: F filters on one FilterSink (src/filternode.hh:262-270).  The forward transform runs once per block; its
 // spectrum (digit-reversed, 64 KB) goes to a CTA-private scratch line in global memory -- written and read back by the
@@ -220,8 +234,8 @@ __global__ void __launch_bounds__(kT, 2) conv8k_kernel(const FilterArgs a, const
     }
     __syncthreads();
     dif_stage2<false>(H0, tab, t);
-    __syncthreads();
-    const int qb = t >> 4, p0 = stage3_pos(t);
+    __syncwarp();                // stage 3 reads what lanes of this warp wrote (see stage3_pos_conv)
+    const int qb = t & 15, p0 = stage3_pos_conv(t);
     if (BANK) {      // forward stage 3 -> the CTA's scratch line
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -236,27 +250,37 @@ __global__ void __launch_bounds__(kT, 2) conv8k_kernel(const FilterArgs a, const
       const float2 *kp = (const float2 *)a.kperm + (size_t)f * 8192 + t;
       // (stage 3,) spectrum multiply, first inverse stage (DFT16 over qc, twiddle conj w_256^(c qb)); the filter
       // spectrum is requested first so that its latency hides behind the shared-memory reads and the DFT
+      {
+        float2 v0[16], v1[16];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float2 *H = h ? H1 : H0;
-        float2 v[16], k[16];
+        for (int h = 0; h < 2; ++h) {
+          float2 *v = h ? v1 : v0;
+          float2 k[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) k[q] = __ldg(kp + (h * 16 + q) * 256);
-        if (BANK) {
+          for (int q = 0; q < 8; ++q) k[q] = __ldg(kp + (h * 16 + q) * 256);
+          if (BANK) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = scratch[(h * 16 + q) * 256];
-        } else {
-          load16(v, H, p0);
-          dft16<false>(v);
+            for (int q = 0; q < 16; ++q) v[q] = scratch[(h * 16 + q) * 256];
+          } else {
+            load16(v, h ? H1 : H0, p0);
+            dft16<false>(v);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = cmulf(v[q], k[q]);
+#pragma unroll
+          for (int q = 8; q < 16; ++q) v[q] = cmulf(v[q], __ldg(kp + (h * 16 + q) * 256));
+          dft16<true>(v);
         }
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = cmulf(v[q], k[q]);
-        dft16<true>(v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = cmulw<true>(v[c], tab[kT2 + 16 * c + qb]);
-        store16(v, H, p0);
+        for (int c = 1; c < 16; ++c) {
+          const float2 w = tab[kT2 + 16 * c + qb];
+          v0[c] = cmulw<true>(v0[c], w);
+          v1[c] = cmulw<true>(v1[c], w);
+        }
+        store16(v0, H0, p0);
+        store16(v1, H1, p0);
       }
-      __syncthreads();
+      __syncwarp();
       {   // second inverse stage: thread t = 16 qa + c, DFT16 over qb, twiddle conj w_4096^(qa (16 b + c))
         const int qa = t >> 4, c = t & 15;
         float2 *B = H0 + pos3(qa, 0, c);
@@ -267,7 +291,7 @@ __global__ void __launch_bounds__(kT, 2) conv8k_kernel(const FilterArgs a, const
         dft16<true>(e);
         dft16<true>(o);
 #pragma unroll
-        for (int b = 0; b < 16; ++b) {
+        for (int b = 0; b < 16; ++b) {         // (w_4096^(qa (16 b + c)) is 1 only for qa = 0: no row to skip here)
           const float2 w = T[16 * b];
           B[pos3(0, b, 0)] = cmulw<true>(e[b], w);
           B[pos3(0, b, 0) + kHalfPad] = cmulw<true>(o[b], w);
@@ -288,7 +312,7 @@ __global__ void __launch_bounds__(kT, 2) conv8k_kernel(const FilterArgs a, const
 #pragma unroll
         for (int q = 0; q < 16; ++q) o[256 * q] = csubf(v[q], z[q]);
       }
-      __syncthreads();           // the buffers are free again: next filter's stage-1 stores / next block's stage 1
+      if (BANK && f + 1 < n_filters) __syncthreads();   // the next filter's first-stage stores; the next BLOCK waits inside dif_stage1
     }
   }
 }
@@ -322,7 +346,8 @@ void fft8k_permute_kernel(const float *kern, float *kperm) {
   for (int h = 0; h < 2; ++h)
     for (int qc = 0; qc < 16; ++qc)
       for (int t = 0; t < 256; ++t) {
-        const int src = 2 * (t + 256 * qc) + h, dst = (h * 16 + qc) * 256 + t;
+        const int m = (t >> 4) + 16 * (t & 15) + 256 * qc;
+        const int src = 2 * m + h, dst = (h * 16 + qc) * 256 + t;
         kperm[2 * dst] = kern[2 * src] * (1.0f / 8192.0f);
         kperm[2 * dst + 1] = kern[2 * src + 1] * (1.0f / 8192.0f);
       }

@@ -13,7 +13,7 @@ dft16 = lambda v, inv: (np.fft.ifft(v, axis=0) * 16 if inv else np.fft.fft(v, ax
 cm = lambda a, tw, inv: a * (np.conj(tw) if inv else tw)
 
 
-def dif_pass(e, o, inv):
+def dif_pass(e, o, inv, conv=False):
     """e, o: [16, 256] register files (index a, thread t = 16 b + c). Returns U_h at [qc, t3], t3 = qa + 16 qb."""
     H = [np.zeros(4096, complex), np.zeros(4096, complex)]
     for h, v in enumerate((e, o)):
@@ -28,9 +28,9 @@ def dif_pass(e, o, inv):
         for q in range(16):
             H[h][256 * qa + 16 * q + c] = cm(v[q], T2[q, c], inv)
     for h in range(2):
-        qa, qb = t & 15, t >> 4
+        qa, qb = (t >> 4, t & 15) if conv else (t & 15, t >> 4)      # conv: warp-local mapping, bins qa + 16 qb + 256 qc
         v = np.stack([H[h][256 * qa + 16 * qb + cc] for cc in range(16)])
-        out.append(dft16(v, inv))          # [qc, t3] = U_h[t3 + 256 qc]
+        out.append(dft16(v, inv))          # [qc, t3] = U_h[qa + 16 qb + 256 qc]
     return out
 
 
@@ -53,14 +53,14 @@ def conv_block(prev, cur, K):
     j = 256 * a + t[None, :]
     e = prev[j] + cur[j]
     o = (prev[j] - cur[j]) * (T8[t][None, :] * T32[a])
-    U = dif_pass(e, o, False)
+    U = dif_pass(e, o, False, conv=True)
     Kp = np.zeros((2, 16, 256), complex)
     for h in range(2):
         for qc in range(16):
-            Kp[h, qc] = K[2 * (t + 256 * qc) + h] / 8192
+            Kp[h, qc] = K[2 * ((t >> 4) + 16 * (t & 15) + 256 * qc) + h] / 8192
     H = [np.zeros(4096, complex), np.zeros(4096, complex)]
     for h in range(2):
-        qa, qb = t & 15, t >> 4
+        qa, qb = t >> 4, t & 15
         v = dft16(U[h] * Kp[h], True)                       # index c'
         for cc in range(16):
             H[h][256 * qa + 16 * qb + cc] = cm(v[cc], T2[cc, qb], True)
