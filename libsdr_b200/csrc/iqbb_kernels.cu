@@ -16,7 +16,7 @@
 //   window accumulators in global memory (L2-resident, 8 B per OUTPUT sample).
 // Kernel 2 (iqbb_finalize_*): one thread per completed window: division / narrowing, optional
 //   fused FM/AM/USB demodulation, carries the open window into the next call.
-#include "iqbb_kernels.cuh"
+#include "iqbb_int_common.cuh"
 #include <atomic>
 #include "demod_math.cuh"
 
@@ -33,24 +33,6 @@ constexpr unsigned kFull = 0xffffffffu;
 __device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }   // 4-byte elements, 8 per thread
 __device__ __forceinline__ int pad64(int i) { return i + (i >> 3); }   // 8-byte elements, 8 per thread
 
-__device__ __forceinline__ void unpack16(uint32_t v, int &re, int &im) {
-  re = (int)(short)(v & 0xffffu);
-  im = ((int)v) >> 16;
-}
-
-// One input sample as packed (re | im << 16) int16 pair.  fmt 0: complex<int16_t> as is; fmt 2/3:
-// AutoCast< complex<int16_t> > fused into the load (src/autocast.hh:187-204): complex uint8 read
-// through an int8_t pointer, (v - 127) << 8 (reference quirk), resp. complex int8, v << 8.
-__device__ __forceinline__ uint32_t load_cs16(const void *base, int64_t idx, uint32_t fmt) {
-  if (fmt == 0) return ((const uint32_t *)base)[idx];
-  if (fmt == 4) return (uint32_t)((const uint16_t *)base)[idx];      // real input: imaginary part 0
-  const char2 s = ((const char2 *)base)[idx];
-  const int bias = fmt == 2 ? 127 : 0;
-  const uint32_t re = (uint32_t)(uint16_t)(int16_t)(((int)s.x - bias) << 8);
-  const uint32_t im = (uint32_t)(uint16_t)(int16_t)(((int)s.y - bias) << 8);
-  return re | (im << 16);
-}
-
 // window bookkeeping (call-relative sample index i): q(i) = r0 + i - (first && i>0); slot = q/ss.
 // n <= 2^30 and r0 < ss <= 2^30, so q and every window bound fit in 32 bits (the 64-bit division
 // this used to be cost more than the FIR itself).
@@ -65,32 +47,6 @@ struct WindowGrid {
     return (int64_t)(uint32_t)((s + 1) * ss - r0 + first);
   }
 };
-
-// ---- shared prologue: zero the next call's accumulators, roll the history ----------------------
-template <typename Sample, typename Acc>
-__device__ __forceinline__ void prologue(const IqbbAccumArgs &a) {
-  Acc *nxt = (Acc *)a.acc_next;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < a.zero_next; k += gridDim.x * blockDim.x) {
-    Acc zero; zero.x = 0; zero.y = 0;
-    nxt[k] = zero;
-  }
-  if (blockIdx.x == 0) {
-    const int64_t H = a.hist_len, n = a.n;
-    if (sizeof(Sample) == 4 && a.in_fmt != 0) {          // fused AutoCast: the history holds raw 8-bit pairs
-      const char2 *x = (const char2 *)a.x, *hi = (const char2 *)a.hist_in;
-      char2 *ho = (char2 *)a.hist_out;
-      for (int64_t k = threadIdx.x; k < H; k += blockDim.x) { const int64_t i = n - H + k; ho[k] = (i >= 0) ? x[i] : hi[H + i]; }
-    } else {
-      const Sample *x = (const Sample *)a.x;
-      const Sample *hi = (const Sample *)a.hist_in;
-      Sample *ho = (Sample *)a.hist_out;
-      for (int64_t k = threadIdx.x; k < H; k += blockDim.x) {
-        const int64_t i = n - H + k;                     // call-relative source index
-        ho[k] = (i >= 0) ? x[i] : hi[H + i];
-      }
-    }
-  }
-}
 
 // Per-window partial sums of one tile from the transposed z staging, added into the call's
 // accumulators.  Short windows (ss <= 64: >= 32 windows per tile) take one THREAD per window --
@@ -231,15 +187,6 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs 
 // its LP+7 packed samples with 128-bit shared loads into registers ONCE, the taps sit in the
 // kernel's parameter (constant) bank so the FIR inner loop is nothing but IMADs with a constant
 // operand plus one unpack per sample -- no loads, no guards, no address arithmetic.
-struct IqbbTaps { int4 t[32]; };
-
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // Persistent CTAs (one per resident slot) walk the tiles grid-stride; the next tile is fetched into
 // the other shared buffer with cp.async (LDGSTS: no registers, no scoreboard stall) while the current
 // one is being filtered, so the global-load latency that used to head every tile is hidden.
@@ -523,6 +470,8 @@ int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st) {
     IqbbTaps taps;
     for (int t = 0; t < 32; ++t) taps.t[t] = make_int4(0, 0, 0, 0);
     for (int t = 0; t < (int)a.taps_len; ++t) taps.t[pad + t] = ((const int4 *)a.host_taps)[t];
+    const int rc = launch_iqbb_accum_warp(scalar, a, taps, lp, st);      // sub_sample >= 16: the barrier-free per-warp kernel
+    if (rc >= 0) return rc;
     if (scalar == SDRG_T_S8) return dispatch_fixed<1>(lp, a, taps, grid, st);
     return a.in_fmt == 4 ? dispatch_fixed<2>(lp, a, taps, grid, st) : dispatch_fixed<0>(lp, a, taps, grid, st);
   }

@@ -33,6 +33,9 @@ struct IqbbAccumArgs {
   uint32_t    in_fmt;     // int16 path only: 0 = complex<int16_t> input, 2 = complex uint8, 3 = complex int8 (fused AutoCast),
                           // 4 = REAL int16 (BaseBand<int16_t>, src/baseband.hh:304): sample = (x, 0)
   uint32_t    fir_shift;  // integer paths: the FIR result is shifted right by this (14 IQBaseBand, 16 BaseBand)
+  uint32_t    div_m, div_s; // per-warp kernel: q / ss == (q * div_m) >> div_s for q < 2^31 (filled in by its launcher)
+  uint32_t    zero;       // always 0: a third addend that keeps the kernel's plain additions on the ALU pipe (IADD3) --
+                          // ptxas otherwise emits them as IMAD.IADD on the multiplier pipe, which is the one that is full
 };
 
 // One process() call of the folded float kernel (iqbb_fold_kernels.cu)

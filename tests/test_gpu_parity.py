@@ -116,6 +116,30 @@ def test_c1_stream_ragged_cuts():
     _stream_case(cfg, x, cuts, DEMOD_FM)
 
 
+@pytest.mark.parametrize("order,ss,Ff,scalar", [
+    (15, 50, 0.0, "s16"),      # 14 stripped taps, real and symmetric: pre-added pairs (kernel variant 4)
+    (16, 50, 0.0, "s16"),      # 15 stripped taps (odd): real taps, two multiplies per tap (variant 3)
+    (31, 16, 0.0, "s16"),      # shortest window the per-warp kernel takes, 30 real symmetric taps
+    (33, 17, 0.0, "s16"),      # 32 taps
+    (15, 300, 0.0, "s16"),     # the warp touches <= 4 windows: REDUX path
+    (9, 2083, 50e3, "s16"),    # complex taps, bank-like window length
+    (15, 64, 0.0, "s8"),       # int8 samples through the per-warp kernel
+    (21, 255, -30e3, "s8"),
+])
+def test_per_warp_kernel_tap_kinds_and_window_lengths(order, ss, Ff, scalar):
+    """iqbb_warp_kernels.cu: every tap kind (complex / real / real symmetric) and both window-sum paths, full-scale
+    input (wrap regime), ragged cuts that split windows and warp tiles anywhere."""
+    cfg = dict(scalar=scalar, Fs=2.4e6, Fc=100e3, Ff=Ff, width=40e3, order=order, sub_sample=ss, oFs=0.0)
+    dt = np.int16 if scalar == "s16" else np.int8
+    full = np.iinfo(dt).max
+    x = synth.iq_int(90000, 2.4e6, [(0.5 * full, 103e3, 0.0), (0.3 * full, 5e3, 0.5), (0.25 * full, -300e3, 1.0)], full // 8, order + ss, dt)
+    if Ff == 0.0 and scalar == "s16":
+        k, _ = gpu_bb(cfg, bs=4096).design()
+        assert np.all(k[:, 1] == 0), "a filter centred on 0 Hz must have real taps"
+    _stream_case(cfg, x, [0, 1, 255, 256, 257, 4095, 30000, 30001, 65536, 89999, 90000], DEMOD_FM)
+    _stream_case(cfg, x, [0, 90000], DEMOD_AM)
+
+
 def test_c1_full_size_buffers():
     """BASELINE config 1 at its real buffer size: 8 buffers of 65536, one launch pair."""
     cfg = dict(synth.C1)
@@ -286,6 +310,8 @@ PATHS = [(1, "direct"), (2, "folded")]
 
 @pytest.mark.parametrize("path", [1, 2, 3], ids=["direct", "folded", "folded-tma"])
 def test_c2_float_chain(path):
+    if path == 3 and not _lib.has_experiments():
+        pytest.skip("the TMA staging variant is compiled only with SDRG_EXPERIMENTS=1")
     cfg = dict(synth.C2)
     x = synth.c2_input(2 << 20)
     e = _float_case(cfg, x, 1 << 20, DEMOD_FM, path)
