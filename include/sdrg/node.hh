@@ -154,6 +154,50 @@ protected:
 };
 
 
+/** Interface of a blocking source (src/node.hh:267-311, src/node.cc:137-190): an input that waits for data from a
+ * device or a file.  next() is driven either by the Queue's idle signal (connect_idle) or by the source's own thread
+ * (parallel); stop_queue_on_eos wires the EOS signal to Queue::stop; both drivers call next() only while the source
+ * is active and the Queue is running.  Deviation: start() raises _is_active.  The reference never sets the flag
+ * (node.cc:154-159; no class derives from BlockingSource there), so its thread would leave _parallel_main at once
+ * and an idle-driven source would never be polled; a subclass that set it beforehand would make start() return
+ * early (`if (_is_active) return`). */
+class BlockingSource : public Source {
+public:
+  BlockingSource(bool parallel = false, bool connect_idle = true, bool stop_queue_on_eos = false)
+    : Source(), _is_active(false), _is_parallel(parallel) {
+    if (!parallel && connect_idle) Queue::get().addIdle(this, &BlockingSource::_nonvirt_idle_cb);
+    if (stop_queue_on_eos) this->addEOS(&Queue::get(), &Queue::stop);
+  }
+  virtual ~BlockingSource() {
+    if (isActive()) stop();
+    if (_thread.joinable()) _thread.join();
+    Queue::get().remIdle(this);
+  }
+  virtual void next() = 0;
+  inline bool isActive() const { return _is_active; }
+  virtual void start() {
+    if (_is_active) return;
+    _is_active = true;
+    if (_is_parallel) {
+      if (_thread.joinable()) _thread.join();
+      _thread = std::thread(&BlockingSource::_parallel_main, this);
+    }
+  }
+  virtual void stop() {
+    if (!_is_active) return;
+    _is_active = false;
+    if (_is_parallel && _thread.joinable()) _thread.join();
+  }
+
+protected:
+  void _parallel_main() { while (_is_active && Queue::get().isRunning()) this->next(); }
+  void _nonvirt_idle_cb() { if (_is_active && Queue::get().isRunning()) this->next(); }
+  volatile bool _is_active;
+  bool _is_parallel;
+  std::thread _thread;
+};
+
+
 /** Forwards config and buffers unchanged (src/node.hh:312-328). */
 class Proxy : public SinkBase, public Source {
 public:

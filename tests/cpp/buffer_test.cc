@@ -67,6 +67,34 @@ int main() {
     try { ConfigError e; e << "x" << 1; throw e; } catch (SDRError &e) { threw = std::string(e.what()) == "x1"; }
     CHECK(threw);
   }
+  {   // BlockingSource (src/node.hh:267-311, node.cc:137-190): idle-driven and parallel, EOS stops the queue
+    // The Queue fires the idle signal once each time it runs dry and then sleeps until a buffer is queued
+    // (src/queue.cc:106-115), so an idle-driven source must feed a QUEUED link from next(), as RTL/Port sources do.
+    struct Count : public Sink<int16_t> { int buffers = 0; virtual void config(const Config &) {} virtual void process(const Buffer<int16_t> &, bool) { ++buffers; } };
+    struct Counter : public BlockingSource {
+      int calls = 0, limit; Buffer<int16_t> buf;
+      Counter(bool parallel, int lim) : BlockingSource(parallel, true, true), limit(lim), buf(8) {}
+      virtual void next() {
+        if (++calls >= limit) { _is_active = false; signalEOS(); return; }
+        send(buf, false);
+      }
+    };
+    {
+      Counter idle(false, 5); Count sink; idle.connect(&sink, false);
+      CHECK(!idle.isActive()); idle.start(); CHECK(idle.isActive());
+      Queue::get().start(); Queue::get().wait();        // next() runs on the idle signal until EOS stops the queue
+      CHECK(idle.calls == 5); CHECK(sink.buffers == 4); CHECK(!idle.isActive()); CHECK(Queue::get().isStopped());
+    }
+    {
+      Counter par(true, 3); Count sink; par.connect(&sink, false);
+      Queue::get().start();
+      while (!Queue::get().isRunning()) {}
+      par.start();                                      // its own thread calls next() while the queue runs
+      Queue::get().wait();
+      par.stop();
+      CHECK(par.calls == 3); CHECK(sink.buffers == 2);
+    }
+  }
   std::printf(failures ? "buffer_test: %d FAILED\n" : "buffer_test: ok\n", failures);
   return failures ? 1 : 0;
 }
