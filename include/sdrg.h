@@ -177,8 +177,11 @@ int sdrg_usbdemod_process(int scalar, const void *in, size_t n, void *out);
 int sdrg_usbdemod_process_dev(int scalar, const void *d_in, size_t n, void *d_out, void *stream);
 
 /* ---- the nodes either side of the path ------------------------------------------
- * AutoCast< std::complex<int16_t> > from complex uint8 / int8 (src/autocast.hh:187-204); n complex
- * samples.  Other casts: SDRG_ERR_CONFIG with the reference's message. */
+ * AutoCast<Scalar> (src/autocast.hh:13-262), the whole table of :30-69: out_type S8 / CS8 / S16 / CS16 from
+ * u8 / s8 / u16 / s16 and, for the complex outputs, cu8 / cs8 / cu16 / cs16; `n` counts input ELEMENTS of in_type
+ * (a complex sample is one element).  Every cast reproduces the reference's arithmetic including its quirks (cu8 read
+ * through int8_t*, the constants (2<<15)-1 and 1<<15).  A pair the reference refuses is SDRG_ERR_CONFIG with its message. */
+int sdrg_autocast_out_bytes(int in_type, int out_type, size_t n, size_t *bytes);   /* bytes n input elements turn into */
 int sdrg_autocast_process(int in_type, int out_type, const void *in, size_t n, void *out);
 int sdrg_autocast_process_dev(int in_type, int out_type, const void *d_in, size_t n, void *d_out, void *stream);
 /* FMDeemph<int16_t> (src/demod.hh:271-362): integer 1-pole IIR with rounding.  `streams` independent
@@ -206,20 +209,31 @@ int sdrg_rxchain_process_dev(sdrg_rxchain *h, const void *d_in, size_t buffer_si
                              void *stream);
 int sdrg_rxchain_process(sdrg_rxchain *h, const void *in, size_t buffer_size, size_t n_buffers,
                          void *bb, void *audio, size_t out_cap, size_t *n_out, size_t *counts);
-/* ---- FFTPlan<float> (src/fftplan.hh:11-34, src/fftplan_fftw3.hh:79-142; FFTW3 is replaced by a
- *      hand-written shared-memory Stockham FFT).  Unnormalised c2c DFT, direction 0 = FORWARD
- *      (exp(-i..)), 1 = BACKWARD.  Sizes: powers of two 2..8192; anything else is SDRG_ERR_CONFIG,
- *      as is an empty buffer (fftplan_fftw3.hh:87-97).  `batch` transforms are contiguous. -------- */
+/* ---- FFTPlan<float> (src/fftplan.hh:11-34, src/fftplan_fftw3.hh:79-142; FFTW3 is replaced by
+ *      hand-written FFT kernels).  Unnormalised c2c DFT, direction 0 = FORWARD (exp(-i..)),
+ *      1 = BACKWARD.  ANY size 1..2^24 like the reference's FFTW plan (fftplan_fftw3.hh:83-106):
+ *      powers of two up to 8192 run in shared memory (the hot sizes), larger powers of two as a
+ *      four-step decomposition, every other size through Bluestein's convolution.  An empty buffer is
+ *      SDRG_ERR_CONFIG (fftplan_fftw3.hh:87-97).  `batch` transforms are contiguous. ---------------- */
 typedef struct sdrg_fft sdrg_fft;
 int sdrg_fft_create(size_t n, int direction, sdrg_fft **h);
 int sdrg_fft_destroy(sdrg_fft *h);
 int sdrg_fft_exec(sdrg_fft *h, const void *in, void *out, size_t batch);
 int sdrg_fft_exec_dev(sdrg_fft *h, const void *d_in, void *d_out, size_t batch, void *stream);
+/* FFTPlan<double> (src/fftplan_fftw3.hh:12-75): complex double, any size 1..2^22, double arithmetic on the device
+ * (radix-2 passes through global memory, Bluestein for sizes that are not a power of two; not a hot path). */
+typedef struct sdrg_fft64 sdrg_fft64;
+int sdrg_fft64_create(size_t n, int direction, sdrg_fft64 **h);
+int sdrg_fft64_destroy(sdrg_fft64 *h);
+int sdrg_fft64_exec(sdrg_fft64 *h, const void *in, void *out, size_t batch);
+int sdrg_fft64_exec_dev(sdrg_fft64 *h, const void *d_in, void *d_out, size_t batch, void *stream);
 
 /* ---- FilterNode<float> (src/filternode.hh:231-283): FilterSink (forward FFT of 2*block, shared) +
  *      one FilterSource per added filter (spectrum multiply, backward FFT, overlap), and the
  *      BufferNode that re-chunks arbitrary input sizes to `block` samples (src/buffernode.hh).
- *      Complex float in, complex float out; block: powers of two 1..4096. ----------------------- */
+ *      Complex float in, complex float out; ANY block size 1..2^22 (filternode.hh:236): powers of two
+ *      up to 4096 run the fused overlap-save kernels, other sizes a gather / batched-FFT / crop
+ *      composition with FFT size 2^ceil(log2 2 block) -- same taps, same normalisation, same result. */
 typedef struct sdrg_filter sdrg_filter;
 int sdrg_filter_create(size_t block_size, sdrg_filter **h);                      /* filternode.hh:236-246 */
 int sdrg_filter_destroy(sdrg_filter *h);

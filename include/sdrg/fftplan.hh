@@ -1,7 +1,7 @@
 // sdrg/fftplan.hh -- FFTPlan<float> and FFT::exec with the reference's surface
-// (src/fftplan.hh:11-34, src/fftplan_fftw3.hh:79-142), executed by libsdrg's shared-memory
-// Stockham FFT instead of FFTW3.  Unnormalised; FORWARD = exp(-i..).  Device restriction: sizes
-// are powers of two, 2..8192 (anything else throws ConfigError, like an empty buffer does).
+// (src/fftplan.hh:11-34, src/fftplan_fftw3.hh:79-142), executed by libsdrg's FFT kernels instead
+// of FFTW3.  Unnormalised; FORWARD = exp(-i..).  Any size 1..2^24 (an empty buffer throws
+// ConfigError like the reference); FFTPlan<double> computes in double on the device as well.
 #ifndef SDRG_FFTPLAN_HH
 #define SDRG_FFTPLAN_HH
 
@@ -40,6 +40,30 @@ public:
 protected:
   Buffer< std::complex<float> > _in, _out;
   sdrg_fft *_h;
+private:
+  FFTPlan(const FFTPlan &);
+  FFTPlan &operator=(const FFTPlan &);
+};
+
+/** FFTPlan<double> (src/fftplan_fftw3.hh:12-75). */
+template <>
+class FFTPlan<double> {
+public:
+  FFTPlan(const Buffer< std::complex<double> > &in, const Buffer< std::complex<double> > &out, FFT::Direction dir)
+    : _in(in), _out(out), _h(0) {
+    if (in.size() != out.size()) { ConfigError err; err << "Can not construct FFT plan: input & output buffers are of different size!"; throw err; }
+    if (in.isEmpty() || out.isEmpty()) { ConfigError err; err << "Can not construct FFT plan: input or output buffer is empty!"; throw err; }
+    gpu::check(sdrg_fft64_create(in.size(), FFT::BACKWARD == dir ? 1 : 0, &_h));
+  }
+  FFTPlan(const Buffer< std::complex<double> > &inplace, FFT::Direction dir) : _in(inplace), _out(inplace), _h(0) {
+    if (inplace.isEmpty()) { ConfigError err; err << "Can not construct FFT plan: Buffer is empty!"; throw err; }
+    gpu::check(sdrg_fft64_create(inplace.size(), FFT::BACKWARD == dir ? 1 : 0, &_h));
+  }
+  virtual ~FFTPlan() { sdrg_fft64_destroy(_h); }
+  void operator()() { gpu::check(sdrg_fft64_exec(_h, _in.data(), _out.data(), 1)); }
+protected:
+  Buffer< std::complex<double> > _in, _out;
+  sdrg_fft64 *_h;
 private:
   FFTPlan(const FFTPlan &);
   FFTPlan &operator=(const FFTPlan &);

@@ -84,6 +84,7 @@ SIGNATURES = {
     "sdrg_iqbb_configure": [_V, _PCFG, _PCFG],
     "sdrg_iqbb_set_float_path": [_V, _I],
     "sdrg_iqbb_set_input_type": [_V, _I],
+    "sdrg_autocast_out_bytes": [_I, _I, _SZ, _PSZ],
     "sdrg_autocast_process": [_I, _I, _V, _SZ, _V],
     "sdrg_autocast_process_dev": [_I, _I, _V, _SZ, _V, _V],
     "sdrg_fmdeemph_create": [_SZ, _PV],
@@ -116,6 +117,10 @@ SIGNATURES = {
     "sdrg_fft_destroy": [_V],
     "sdrg_fft_exec": [_V, _V, _V, _SZ],
     "sdrg_fft_exec_dev": [_V, _V, _V, _SZ, _V],
+    "sdrg_fft64_create": [_SZ, _I, _PV],
+    "sdrg_fft64_destroy": [_V],
+    "sdrg_fft64_exec": [_V, _V, _V, _SZ],
+    "sdrg_fft64_exec_dev": [_V, _V, _V, _SZ, _V],
     "sdrg_filter_create": [_SZ, _PV],
     "sdrg_filter_destroy": [_V],
     "sdrg_filter_add": [_V, _D, _D, _PSZ],

@@ -1074,22 +1074,71 @@ int sdrg_amdemod_process(int scalar, const void *in, size_t n, void *out) { retu
 int sdrg_usbdemod_process(int scalar, const void *in, size_t n, void *out) { return envelope_host(true, scalar, in, n, out); }
 
 // ---- AutoCast / FMDeemph ----------------------------------------------------------------------------
-int sdrg_autocast_process_dev(int in_type, int out_type, const void *d_in, size_t n, void *d_out, void *stream) {
-  if (out_type != SDRG_T_CS16 || (in_type != SDRG_T_CU8 && in_type != SDRG_T_CS8))
+// (in_type, out_type) -> cast kind of demod_kernels.cu (0 = identity, -1 = the reference refuses the pair), bytes per
+// input element, output bytes per input element  (src/autocast.hh:30-69)
+static int cast_kind(int in_type, int out_type, size_t *in_elem, size_t *out_per_in, size_t *scalars_per_elem) {
+  static const size_t elem[] = {0, 1, 1, 2, 2, 4, 8, 2, 2, 4, 4, 8, 16};
+  if (in_type < SDRG_T_U8 || in_type > SDRG_T_CF64) return -1;
+  *in_elem = elem[in_type];
+  const bool cin = in_type >= SDRG_T_CU8;
+  *scalars_per_elem = cin ? 2 : 1;
+  int k = -1;
+  switch (out_type) {
+    case SDRG_T_S8:
+      k = in_type == SDRG_T_U8 ? 1 : in_type == SDRG_T_S8 ? 0 : in_type == SDRG_T_U16 ? 2 : in_type == SDRG_T_S16 ? 3 : -1; break;
+    case SDRG_T_CS8:
+      k = in_type == SDRG_T_U8 ? 4 : in_type == SDRG_T_S8 ? 5 : in_type == SDRG_T_CU8 ? 1 : in_type == SDRG_T_CS8 ? 0 :
+          in_type == SDRG_T_U16 ? 6 : in_type == SDRG_T_S16 ? 7 : in_type == SDRG_T_CU16 ? 2 : in_type == SDRG_T_CS16 ? 3 : -1; break;
+    case SDRG_T_S16:
+      k = in_type == SDRG_T_U8 ? 8 : in_type == SDRG_T_S8 ? 9 : in_type == SDRG_T_U16 ? 10 : in_type == SDRG_T_S16 ? 0 : -1; break;
+    case SDRG_T_CS16:
+      k = in_type == SDRG_T_U8 ? 11 : in_type == SDRG_T_S8 ? 12 : in_type == SDRG_T_CU8 ? 8 : in_type == SDRG_T_CS8 ? 9 :
+          in_type == SDRG_T_U16 ? 13 : in_type == SDRG_T_S16 ? 14 : in_type == SDRG_T_CU16 ? 10 : in_type == SDRG_T_CS16 ? 0 : -1; break;
+    default: break;
+  }
+  if (k < 0) return -1;
+  const size_t out_scalar = (out_type == SDRG_T_S8 || out_type == SDRG_T_CS8) ? 1 : 2;
+  const bool complexify = (k >= 4 && k <= 7) || k >= 11;          // real scalar in, complex value out
+  *out_per_in = k == 0 ? *in_elem : (*scalars_per_elem) * out_scalar * (complexify ? 2 : 1);
+  return k;
+}
+
+int sdrg_autocast_out_bytes(int in_type, int out_type, size_t n, size_t *bytes) {
+  size_t ie = 0, opi = 0, spe = 0;
+  if (!bytes) return set_error(SDRG_ERR_ARG, "null argument");
+  if (cast_kind(in_type, out_type, &ie, &opi, &spe) < 0)
     return set_error(SDRG_ERR_CONFIG, "AutoCast: Can not cast from type %s (%d) to %s (%d)", type_name(in_type), in_type,
                      type_name(out_type), out_type);
-  return launch_autocast_cs16(in_type == SDRG_T_CU8 ? 2 : 3, d_in, 2 * n, d_out, (cudaStream_t)stream);
+  *bytes = n * opi;
+  return SDRG_OK;
+}
+int sdrg_autocast_process_dev(int in_type, int out_type, const void *d_in, size_t n, void *d_out, void *stream) {
+  size_t ie = 0, opi = 0, spe = 0;
+  const int k = cast_kind(in_type, out_type, &ie, &opi, &spe);
+  if (k < 0)
+    return set_error(SDRG_ERR_CONFIG, "AutoCast: Can not cast from type %s (%d) to %s (%d)", type_name(in_type), in_type,
+                     type_name(out_type), out_type);
+  if (k == 0) {                   // _identity: the bytes as they are
+    if (n && d_in != d_out) SDRG_CUDA(cudaMemcpyAsync(d_out, d_in, n * ie, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SDRG_OK;
+  }
+  return launch_autocast(k, d_in, n * spe, d_out, (cudaStream_t)stream);
 }
 int sdrg_autocast_process(int in_type, int out_type, const void *in, size_t n, void *out) {
   if (!n) return SDRG_OK;
+  size_t ie = 0, opi = 0, spe = 0;
+  if (cast_kind(in_type, out_type, &ie, &opi, &spe) < 0)
+    return set_error(SDRG_ERR_CONFIG, "AutoCast: Can not cast from type %s (%d) to %s (%d)", type_name(in_type), in_type,
+                     type_name(out_type), out_type);
   SDRG_CUDA(cudaSetDevice(g_device));
+  const size_t ib = n * ie, ob = n * opi, off = (ib + 15) & ~(size_t)15;
   void *d = nullptr;
-  int rc = sdrg_scratch(2 * n + 4 * n, &d);
+  int rc = sdrg_scratch(off + ob, &d);
   if (rc) return rc;
-  SDRG_CUDA(cudaMemcpy(d, in, 2 * n, cudaMemcpyHostToDevice));
-  rc = sdrg_autocast_process_dev(in_type, out_type, d, n, (char *)d + ((2 * n + 15) & ~(size_t)15), 0);
+  SDRG_CUDA(cudaMemcpy(d, in, ib, cudaMemcpyHostToDevice));
+  rc = sdrg_autocast_process_dev(in_type, out_type, d, n, (char *)d + off, 0);
   if (rc) return rc;
-  SDRG_CUDA(cudaMemcpy(out, (char *)d + ((2 * n + 15) & ~(size_t)15), 4 * n, cudaMemcpyDeviceToHost));
+  SDRG_CUDA(cudaMemcpy(out, (char *)d + off, ob, cudaMemcpyDeviceToHost));
   return SDRG_OK;
 }
 

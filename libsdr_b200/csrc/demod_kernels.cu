@@ -144,6 +144,53 @@ int launch_autocast_cs16(int fmt, const void *in, size_t n_bytes, void *out, cud
   return SDRG_OK;
 }
 
+// ---- the whole AutoCast table (src/autocast.hh:30-69; cast functions :120-262) -----------------------------------------
+// One input SCALAR per thread-iteration; kinds 1-3 and 8-10 write one scalar, the others a complex value with a zero
+// imaginary part.  The arithmetic restates the reference's expressions (their widths, the int8_t* reinterpretation in
+// _uint8_int16, the constants (2<<15)-1 and 1<<15); every pair is checked against bytes the reference itself produced
+// (tests/golden/cast_table.npz).
+template <int KIND>
+__global__ void __launch_bounds__(256) autocast_kernel(const void *__restrict__ in, size_t n, void *__restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int v;
+    if (KIND == 1 || KIND == 4 || KIND == 11) v = (int)((const unsigned char *)in)[i];
+    else if (KIND == 5 || KIND == 8 || KIND == 9 || KIND == 12) v = (int)((const signed char *)in)[i];
+    else if (KIND == 2 || KIND == 10 || KIND == 13) v = (int)((const unsigned short *)in)[i];
+    else v = (int)((const short *)in)[i];                                   // 3, 6 (uint16 read as int16), 7, 14
+    int r;
+    switch (KIND) {
+      case 1: case 4: r = v - 127; break;
+      case 2: r = (v >> 8) - 127; break;
+      case 3: case 7: r = v >> 8; break;
+      case 5: case 14: r = v; break;
+      case 6: r = (v >> 8) - 65535; break;
+      case 8: case 11: r = (int)((unsigned)(v - 127) << 8); break;
+      case 9: case 12: r = (int)((unsigned)v << 8); break;
+      case 10: r = v - 65535; break;
+      default: r = v - 32768; break;                                        // 13
+    }
+    if (KIND <= 3) ((signed char *)out)[i] = (signed char)r;
+    else if (KIND <= 7) ((char2 *)out)[i] = make_char2((signed char)r, 0);
+    else if (KIND <= 10) ((short *)out)[i] = (short)r;
+    else ((short2 *)out)[i] = make_short2((short)r, 0);
+  }
+}
+
+int launch_autocast(int kind, const void *in, size_t n_scalars, void *out, cudaStream_t st) {
+  if (n_scalars == 0) return SDRG_OK;
+  const unsigned g = grid_for(n_scalars);
+  switch (kind) {
+#define SDRG_CASE(K) case K: autocast_kernel<K><<<g, 256, 0, st>>>(in, n_scalars, out); break;
+    SDRG_CASE(1) SDRG_CASE(2) SDRG_CASE(3) SDRG_CASE(4) SDRG_CASE(5) SDRG_CASE(6) SDRG_CASE(7)
+    SDRG_CASE(8) SDRG_CASE(9) SDRG_CASE(10) SDRG_CASE(11) SDRG_CASE(12) SDRG_CASE(13) SDRG_CASE(14)
+#undef SDRG_CASE
+    default: return set_error(SDRG_ERR_ARG, "AutoCast: unknown cast kind %d", kind);
+  }
+  SDRG_CHECK_LAUNCH("autocast_kernel");
+  return SDRG_OK;
+}
+
 int launch_fmdeemph(const void *in, void *out, size_t n, size_t streams, size_t stride, int alpha, void *avg, cudaStream_t st) {
   if (n == 0 || streams == 0) return SDRG_OK;
   fmdeemph_kernel<<<(unsigned)((streams + 127) / 128), 128, 0, st>>>((const short *)in, (short *)out, n, streams, stride, alpha, (short *)avg);

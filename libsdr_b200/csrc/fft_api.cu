@@ -69,14 +69,13 @@ int upload_tab8k(void **d_tab) {
 
 struct sdrg_fft {
   int device = 0;
-  size_t n = 0; int log2n = 0; int inverse = 0;
-  void *d_tw = nullptr;
-  void *d_tab8k = nullptr;               // n = 4096 / 8192: tables of fft8k_kernels.cu
+  size_t n = 0; int inverse = 0;
+  AnyFft *plan = nullptr;                // shared-memory kernels (2..8192), four-step, or Bluestein (fft_general.cu)
   cudaStream_t stream = nullptr;
   void *d_in = nullptr, *d_out = nullptr; size_t cap = 0;
 };
 
-struct FilterBand { double fmin, fmax; std::vector<float> taps, kern; };
+struct FilterBand { double fmin, fmax; std::vector<float> taps, kern, kern_m; };   // kern: 2B-point spectrum; kern_m: M-point (general path)
 
 struct sdrg_filter {
   int device = 0;
@@ -86,6 +85,7 @@ struct sdrg_filter {
   std::vector<FilterBand> bands;
   void *d_tw = nullptr, *d_kern = nullptr; bool kern_dirty = true;
   void *d_kperm = nullptr, *d_tab8k = nullptr;         // block 4096: permuted spectra + tables of fft8k_kernels.cu
+  GeneralOla *gen = nullptr;                           // blocks that are not a power of two <= 4096 (fft_general.cu)
   void *d_hist[2] = {nullptr, nullptr}; int parity = 0;
   void *d_pend = nullptr; size_t pending = 0;          // re-chunking (BufferNode): < block samples waiting
   void *d_stage = nullptr; size_t stage_cap = 0;
@@ -96,24 +96,52 @@ struct sdrg_filter {
 
 namespace {
 
+// O(n^2) DFT in double with exact phase reduction (config time, sizes that are not a power of two)
+void host_dft(std::vector<std::complex<double> > &a) {
+  const size_t n = a.size();
+  std::vector<std::complex<double> > w(n), out(n);
+  for (size_t k = 0; k < n; ++k) w[k] = std::polar(1.0, -2.0 * M_PI * (double)k / (double)n);
+  for (size_t k = 0; k < n; ++k) {
+    std::complex<double> acc(0, 0);
+    size_t idx = 0;
+    for (size_t j = 0; j < n; ++j) { acc += a[j] * w[idx]; idx += k; if (idx >= n) idx -= n; }
+    out[k] = acc;
+  }
+  a.swap(out);
+}
+
 int design_band(sdrg_filter *h, FilterBand &b) {
   const size_t N = h->block;
   const double Fs = h->Fs;
   const double fmin = std::max(b.fmin, -Fs / 2), fmax = std::min(b.fmax, Fs / 2);
   const double bw = fmax - fmin, Fc = fmin + bw / 2;
   b.taps.assign(2 * N, 0.f);
+  b.kern.clear(); b.kern_m.clear();
+  double e2 = 0;
   std::vector<std::complex<double> > z(2 * N, std::complex<double>(0, 0));
   for (size_t i = 0; i < N; ++i) {
     const std::complex<float> v = sinc_tap((int)i, (int)N, Fc, bw, Fs);
     b.taps[2 * i] = v.real(); b.taps[2 * i + 1] = v.imag();
     z[i] = std::complex<double>(v.real(), v.imag());
+    e2 += std::norm(z[i]);
   }
-  host_fft(z);
-  double nrm2 = 0;
-  for (size_t i = 0; i < 2 * N; ++i) nrm2 += std::norm(z[i]);
-  const double nrm = std::sqrt(nrm2);
-  b.kern.resize(4 * N);
-  for (size_t i = 0; i < 2 * N; ++i) { b.kern[2 * i] = (float)(z[i].real() / nrm); b.kern[2 * i + 1] = (float)(z[i].imag() / nrm); }
+  // l2 norm of the 2N-point spectrum (Buffer::norm2, src/buffer.hh:182-188) = sqrt(2N) |h|_2 by Parseval
+  const double nrm = std::sqrt(2.0 * (double)N * e2);
+  if (h->gen) {                 // general path: the same taps on the M-point grid
+    const size_t M = h->gen->M;
+    std::vector<std::complex<double> > zm(M, std::complex<double>(0, 0));
+    for (size_t i = 0; i < N; ++i) zm[i] = z[i];
+    host_fft(zm);
+    b.kern_m.resize(2 * M);
+    for (size_t i = 0; i < M; ++i) { b.kern_m[2 * i] = (float)(zm[i].real() / nrm); b.kern_m[2 * i + 1] = (float)(zm[i].imag() / nrm); }
+  }
+  if (pow2(2 * N)) host_fft(z);
+  else if (2 * N <= 16384) host_dft(z);
+  else z.clear();                // the reference-shaped 2N-point spectrum is for inspection only; too slow to form here
+  if (!z.empty()) {
+    b.kern.resize(4 * N);
+    for (size_t i = 0; i < 2 * N; ++i) { b.kern[2 * i] = (float)(z[i].real() / nrm); b.kern[2 * i + 1] = (float)(z[i].imag() / nrm); }
+  }
   h->kern_dirty = true;
   return SDRG_OK;
 }
@@ -123,7 +151,12 @@ int upload_kernels(sdrg_filter *h) {
   const size_t n2 = 2 * h->block, F = h->bands.size();
   if (h->d_kern) { SDRG_CUDA(cudaDeviceSynchronize()); cudaFree(h->d_kern); h->d_kern = nullptr; }
   if (h->d_kperm) { cudaFree(h->d_kperm); h->d_kperm = nullptr; }
-  if (F) {
+  if (F && h->gen) {            // general path: M-point spectra
+    const size_t M = h->gen->M;
+    SDRG_CUDA(cudaMalloc(&h->d_kern, F * M * 2 * sizeof(float)));
+    for (size_t f = 0; f < F; ++f)
+      SDRG_CUDA(cudaMemcpy((float *)h->d_kern + f * M * 2, h->bands[f].kern_m.data(), M * 2 * sizeof(float), cudaMemcpyHostToDevice));
+  } else if (F) {
     SDRG_CUDA(cudaMalloc(&h->d_kern, F * n2 * 2 * sizeof(float)));
     for (size_t f = 0; f < F; ++f)
       SDRG_CUDA(cudaMemcpy((float *)h->d_kern + f * n2 * 2, h->bands[f].kern.data(), n2 * 2 * sizeof(float), cudaMemcpyHostToDevice));
@@ -164,14 +197,12 @@ int sdrg_fft_create(size_t n, int direction, sdrg_fft **out) {
   if (!out) return set_error(SDRG_ERR_ARG, "null argument");
   *out = nullptr;
   if (n == 0) return set_error(SDRG_ERR_CONFIG, "Can not construct FFT plan: Buffer is empty!");      // fftplan_fftw3.hh:93-97
-  if (!pow2(n) || n > ((size_t)1 << kFftMaxLog2) || n < 2)
-    return set_error(SDRG_ERR_CONFIG, "FFT plan: size %zu is not supported on the device (powers of two, 2..%d)", n, 1 << kFftMaxLog2);
   sdrg_fft *h = new sdrg_fft();
   int dev = 0; cudaGetDevice(&dev);
-  h->device = dev; h->n = n; h->log2n = ilog2(n); h->inverse = direction ? 1 : 0;
-  int rc = upload_twiddles(n, &h->d_tw);
-  if (rc == SDRG_OK && (n == 4096 || n == 8192)) rc = upload_tab8k(&h->d_tab8k);
-  if (rc) { cudaFree(h->d_tw); delete h; return rc; }
+  h->device = dev; h->n = n; h->inverse = direction ? 1 : 0;
+  h->plan = new AnyFft();
+  const int rc = h->plan->init(n);
+  if (rc) { delete h->plan; delete h; return rc; }
   *out = h;
   return SDRG_OK;
 }
@@ -179,15 +210,15 @@ int sdrg_fft_destroy(sdrg_fft *h) {
   if (!h) return SDRG_OK;
   cudaSetDevice(h->device); cudaDeviceSynchronize();
   if (h->stream) cudaStreamDestroy(h->stream);
-  cudaFree(h->d_tw); cudaFree(h->d_tab8k); cudaFree(h->d_in); cudaFree(h->d_out);
+  delete h->plan;
+  cudaFree(h->d_in); cudaFree(h->d_out);
   delete h;
   return SDRG_OK;
 }
 int sdrg_fft_exec_dev(sdrg_fft *h, const void *d_in, void *d_out, size_t batch, void *stream) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
   SDRG_CUDA(cudaSetDevice(h->device));
-  if (h->d_tab8k) return launch_fft8k(d_in, d_out, (int)h->n, h->inverse, batch, h->d_tab8k, (cudaStream_t)stream);
-  return launch_fft_batch(d_in, d_out, (int)h->n, h->log2n, h->inverse, batch, h->d_tw, (cudaStream_t)stream);
+  return h->plan->exec(d_in, d_out, batch, h->inverse, (cudaStream_t)stream);
 }
 int sdrg_fft_exec(sdrg_fft *h, const void *in, void *out, size_t batch) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
@@ -208,16 +239,69 @@ int sdrg_fft_exec(sdrg_fft *h, const void *in, void *out, size_t batch) {
   return SDRG_OK;
 }
 
+// ---- FFTPlan<double> ------------------------------------------------------------------------------
+struct sdrg_fft64_impl { int device; int inverse; Fft64 plan; cudaStream_t stream; void *d_in, *d_out; size_t cap; };
+int sdrg_fft64_create(size_t n, int direction, sdrg_fft64 **out) {
+  if (!out) return set_error(SDRG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (n == 0) return set_error(SDRG_ERR_CONFIG, "Can not construct FFT plan: Buffer is empty!");      // fftplan_fftw3.hh:27-31
+  sdrg_fft64_impl *h = new sdrg_fft64_impl();
+  h->device = 0; cudaGetDevice(&h->device);
+  h->inverse = direction ? 1 : 0; h->stream = nullptr; h->d_in = h->d_out = nullptr; h->cap = 0;
+  const int rc = h->plan.init(n);
+  if (rc) { delete h; return rc; }
+  *out = (sdrg_fft64 *)h;
+  return SDRG_OK;
+}
+int sdrg_fft64_destroy(sdrg_fft64 *hh) {
+  sdrg_fft64_impl *h = (sdrg_fft64_impl *)hh;
+  if (!h) return SDRG_OK;
+  cudaSetDevice(h->device); cudaDeviceSynchronize();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaFree(h->d_in); cudaFree(h->d_out);
+  delete h;
+  return SDRG_OK;
+}
+int sdrg_fft64_exec_dev(sdrg_fft64 *hh, const void *d_in, void *d_out, size_t batch, void *stream) {
+  sdrg_fft64_impl *h = (sdrg_fft64_impl *)hh;
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  SDRG_CUDA(cudaSetDevice(h->device));
+  return h->plan.exec(d_in, d_out, batch, h->inverse, (cudaStream_t)stream);
+}
+int sdrg_fft64_exec(sdrg_fft64 *hh, const void *in, void *out, size_t batch) {
+  sdrg_fft64_impl *h = (sdrg_fft64_impl *)hh;
+  if (!h) return set_error(SDRG_ERR_ARG, "null handle");
+  if (!batch) return SDRG_OK;
+  SDRG_CUDA(cudaSetDevice(h->device));
+  int rc = own_stream(&h->stream);
+  if (rc) return rc;
+  const size_t bytes = batch * h->plan.n * 2 * sizeof(double);
+  if (h->cap < bytes) {
+    if (h->d_in) { cudaFree(h->d_in); cudaFree(h->d_out); h->d_in = h->d_out = nullptr; }
+    SDRG_CUDA(cudaMalloc(&h->d_in, bytes)); SDRG_CUDA(cudaMalloc(&h->d_out, bytes)); h->cap = bytes;
+  }
+  SDRG_CUDA(cudaMemcpyAsync(h->d_in, in, bytes, cudaMemcpyHostToDevice, h->stream));
+  rc = sdrg_fft64_exec_dev(hh, h->d_in, h->d_out, batch, h->stream);
+  if (rc) return rc;
+  SDRG_CUDA(cudaMemcpyAsync(out, h->d_out, bytes, cudaMemcpyDeviceToHost, h->stream));
+  SDRG_CUDA(cudaStreamSynchronize(h->stream));
+  return SDRG_OK;
+}
+
 // ---- FilterNode -------------------------------------------------------------------------------------
 int sdrg_filter_create(size_t block_size, sdrg_filter **out) {
   if (!out) return set_error(SDRG_ERR_ARG, "null argument");
   *out = nullptr;
-  if (!pow2(block_size) || 2 * block_size > ((size_t)1 << kFftMaxLog2) || block_size < 1)
-    return set_error(SDRG_ERR_CONFIG, "FilterNode: block size %zu is not supported on the device (powers of two, 1..%d)",
-                     block_size, 1 << (kFftMaxLog2 - 1));
+  if (block_size < 1 || block_size > ((size_t)1 << 22))
+    return set_error(SDRG_ERR_CONFIG, "FilterNode: block size %zu is not supported on the device (1..%d)", block_size, 1 << 22);
   sdrg_filter *h = new sdrg_filter();
   int dev = 0; cudaGetDevice(&dev);
   h->device = dev; h->block = block_size; h->log2n = ilog2(2 * block_size);
+  if (!pow2(block_size) || 2 * block_size > ((size_t)1 << kFftMaxLog2)) {      // not a fused-kernel size
+    h->gen = new GeneralOla();
+    const int rc = h->gen->init(block_size);
+    if (rc) { delete h->gen; delete h; return rc; }
+  }
   *out = h;
   return SDRG_OK;
 }
@@ -227,6 +311,7 @@ int sdrg_filter_destroy(sdrg_filter *h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->d_tw); cudaFree(h->d_kern); cudaFree(h->d_kperm); cudaFree(h->d_tab8k); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]);
   cudaFree(h->d_pend); cudaFree(h->d_stage); cudaFree(h->d_spec); cudaFree(h->d_in); cudaFree(h->d_out);
+  delete h->gen;
   delete h;
   return SDRG_OK;
 }
@@ -263,11 +348,12 @@ int sdrg_filter_configure(sdrg_filter *h, const sdrg_config *src, sdrg_config *o
   SDRG_CUDA(cudaDeviceSynchronize());
   h->Fs = src->sample_rate;
   for (size_t f = 0; f < h->bands.size(); ++f) design_band(h, h->bands[f]);
-  if (!h->d_tw) { int rc = upload_twiddles(2 * h->block, &h->d_tw); if (rc) return rc; }
+  if (!h->d_tw && !h->gen) { int rc = upload_twiddles(2 * h->block, &h->d_tw); if (rc) return rc; }
   const size_t hb = h->block * 2 * sizeof(float);
+  const size_t hist_b = (h->gen ? h->gen->M - h->block : h->block) * 2 * sizeof(float);   // general path: M - B samples of history
   for (int k = 0; k < 2; ++k) {
-    if (!h->d_hist[k]) SDRG_CUDA(cudaMalloc(&h->d_hist[k], hb));
-    SDRG_CUDA(cudaMemset(h->d_hist[k], 0, hb));                 // _last_trafo zeroed, filternode.hh:117-119
+    if (!h->d_hist[k]) SDRG_CUDA(cudaMalloc(&h->d_hist[k], hist_b));
+    SDRG_CUDA(cudaMemset(h->d_hist[k], 0, hist_b));             // _last_trafo zeroed, filternode.hh:117-119
   }
   if (!h->d_pend) SDRG_CUDA(cudaMalloc(&h->d_pend, hb));
   h->pending = 0; h->parity = 0;
@@ -277,7 +363,9 @@ int sdrg_filter_configure(sdrg_filter *h, const sdrg_config *src, sdrg_config *o
 }
 int sdrg_filter_get_design(const sdrg_filter *h, size_t index, void *kern_2n, void *taps_n) {
   if (!h) return set_error(SDRG_ERR_ARG, "null handle");
-  if (index >= h->bands.size() || h->bands[index].kern.empty()) return set_error(SDRG_ERR_RUNTIME, "FilterNode: filter %zu not designed yet", index);
+  if (index >= h->bands.size() || h->bands[index].taps.empty()) return set_error(SDRG_ERR_RUNTIME, "FilterNode: filter %zu not designed yet", index);
+  if (kern_2n && h->bands[index].kern.empty())
+    return set_error(SDRG_ERR_RUNTIME, "FilterNode: the 2N-point spectrum is not formed for block sizes that are neither a power of two nor <= 8192");
   if (kern_2n) memcpy(kern_2n, h->bands[index].kern.data(), h->bands[index].kern.size() * sizeof(float));
   if (taps_n) memcpy(taps_n, h->bands[index].taps.data(), h->block * 2 * sizeof(float));
   return SDRG_OK;
@@ -312,7 +400,11 @@ int sdrg_filter_process_dev(sdrg_filter *h, const void *d_in, size_t n_in, void 
       src = (const char *)h->d_stage;
     }
   }
-  if (nblk) {
+  if (nblk && h->gen) {
+    rc = h->gen->run(src, nblk, h->d_hist[h->parity], h->d_hist[h->parity ^ 1], h->d_kern, (int)h->bands.size(), d_out, out_stride, st);
+    if (rc) return rc;
+    h->parity ^= 1;
+  } else if (nblk) {
     FilterArgs a{};
     a.x = src; a.hist_in = h->d_hist[h->parity]; a.hist_out = h->d_hist[h->parity ^ 1];
     a.kern = h->d_kern; a.out = d_out; a.out_stride = out_stride; a.tw = h->d_tw;

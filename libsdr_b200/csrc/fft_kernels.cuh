@@ -35,4 +35,40 @@ int launch_fft8k(const void *in, void *out, int n, int inverse, size_t batch, co
 int launch_conv8k(const FilterArgs &a, size_t n_blocks, cudaStream_t st);
 int conv8k_grid(size_t n_blocks);   // CTAs that launch will use: a filter bank needs 64 KB of FilterArgs::spec per CTA
 
+
+// fft_general.cu: every other size, composed from the kernels above (see its header comment)
+struct Pow2Fft {          // n = 2^L >= 2: shared-memory kernels up to 8192, four-step above (up to 2^26)
+  size_t n = 0; int log2n = 0;
+  void *d_tw = nullptr, *d_tab8k = nullptr;
+  size_t n1 = 0, n2 = 0; Pow2Fft *sub1 = nullptr, *sub2 = nullptr;
+  void *d_tw_hi = nullptr, *d_tw_lo = nullptr, *d_s0 = nullptr, *d_s1 = nullptr; size_t cap0 = 0, cap1 = 0;
+  ~Pow2Fft();
+  int init(size_t n);
+  int exec(const void *in, void *out, size_t batch, int inverse, cudaStream_t st);   // in == out allowed
+};
+struct AnyFft {           // any n >= 1: Pow2Fft directly or through Bluestein's convolution of length M
+  size_t n = 0, M = 0; Pow2Fft *p2 = nullptr;
+  void *d_chirp = nullptr, *d_ghat = nullptr, *d_a = nullptr; size_t cap_a = 0;
+  ~AnyFft();
+  int init(size_t n);
+  int exec(const void *in, void *out, size_t batch, int inverse, cudaStream_t st);
+};
+struct GeneralOla {       // FilterNode block B (any), FFT size M = 2^ceil(log2 2B), history M - B samples
+  size_t B = 0, M = 0; Pow2Fft *p2 = nullptr;
+  void *d_seg = nullptr, *d_work = nullptr; size_t cap_seg = 0, cap_work = 0;
+  ~GeneralOla();
+  int init(size_t block);
+  int run(const void *x, size_t n_blocks, const void *hist_in, void *hist_out, const void *kern_M, int n_filters,
+          void *out, size_t out_stride, cudaStream_t st);
+};
+
+struct Fft64 {            // FFTPlan<double>: any n <= 2^22, radix-2 global-memory passes (+ Bluestein), double arithmetic
+  size_t n = 0, M = 0;
+  void *d_tw = nullptr, *d_chirp = nullptr, *d_ghat = nullptr, *d_a = nullptr, *d_b = nullptr; size_t cap_a = 0, cap_b = 0;
+  ~Fft64();
+  int init(size_t n);
+  int exec(const void *in, void *out, size_t batch, int inverse, cudaStream_t st);
+  int pow2_inplace(size_t batch, int inverse, cudaStream_t st);
+};
+
 }  // namespace sdrg

@@ -115,6 +115,8 @@ int launch_amdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t
 int launch_usbdemod(int scalar, const void *in, size_t n, void *out, cudaStream_t st);
 // AutoCast<complex<int16_t>> from complex uint8 (fmt 2) / int8 (fmt 3): n_bytes in, n_bytes int16 out
 int launch_autocast_cs16(int fmt, const void *in, size_t n_bytes, void *out, cudaStream_t st);
+// the whole AutoCast table: kind 1..14 (demod_kernels.cu), n_scalars input scalars
+int launch_autocast(int kind, const void *in, size_t n_scalars, void *out, cudaStream_t st);
 // FMDeemph<int16_t>: `streams` independent sequences of n samples (stride elements apart), one thread each
 int launch_fmdeemph(const void *in, void *out, size_t n, size_t streams, size_t stride, int alpha, void *avg, cudaStream_t st);
 

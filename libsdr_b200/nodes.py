@@ -360,6 +360,30 @@ class FFTPlan:
         return out
 
 
+class FFTPlan64:
+    """FFTPlan<double> (src/fftplan_fftw3.hh:12-75): complex128 in / out, any size."""
+    FORWARD, BACKWARD = 0, 1
+
+    def __init__(self, n, direction):
+        self.n = int(n)
+        self._h = C.c_void_p()
+        _lib.call("sdrg_fft64_create", self.n, int(direction), C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().sdrg_fft64_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def __call__(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        out = np.empty_like(x)
+        _lib.call("sdrg_fft64_exec", self._h, _np_ptr(x), _np_ptr(out), x.size // self.n)
+        return out
+
+
 class FilterNode:
     """FilterNode<float>(block_size) (src/filternode.hh:231-283): addFilter(fmin, fmax) returns the
     filter's index; process(x) returns an array (n_filters, n_out) of complex64."""
@@ -573,6 +597,27 @@ def autocast_cs16(x):
     out = np.zeros(x.shape, dtype=np.int16)
     _lib.call("sdrg_autocast_process", t, _lib.T_CS16, _np_ptr(x), x.shape[0], _np_ptr(out))
     return out
+
+
+def autocast(x, in_type, out_type):
+    """AutoCast<out_type> (src/autocast.hh:30-69) of a numpy array / CUDA tensor holding elements of `in_type`
+    (Config::Type ids, _lib.T_*).  Returns the output as raw uint8 bytes (numpy) or a uint8 tensor."""
+    in_elem = [0, 1, 1, 2, 2, 4, 8, 2, 2, 4, 4, 8, 16][int(in_type)]
+    nbytes = C.c_size_t(0)
+    if _is_torch(x):
+        import torch
+        raw = x.contiguous().view(torch.uint8).reshape(-1)
+        n = raw.numel() // in_elem
+        _lib.call("sdrg_autocast_out_bytes", int(in_type), int(out_type), n, C.byref(nbytes))
+        out = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=x.device)
+        _lib.call("sdrg_autocast_process_dev", int(in_type), int(out_type), _dev_in(raw), n, C.c_void_p(out.data_ptr()), _stream_ptr())
+        return out[:nbytes.value]
+    raw = np.ascontiguousarray(x).view(np.uint8).reshape(-1)
+    n = raw.size // in_elem
+    _lib.call("sdrg_autocast_out_bytes", int(in_type), int(out_type), n, C.byref(nbytes))
+    out = np.zeros(max(nbytes.value, 1), dtype=np.uint8)
+    _lib.call("sdrg_autocast_process", int(in_type), int(out_type), _np_ptr(raw), n, _np_ptr(out))
+    return out[:nbytes.value]
 
 
 class FMDeemph:

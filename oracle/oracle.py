@@ -235,6 +235,62 @@ def autocast_cs16(x):
     return out
 
 
+# ---- the whole AutoCast table (src/autocast.hh:30-69, cast functions :120-262) ---------------------------------
+# Config::Type ids (src/node.hh:39-53)
+T_U8, T_S8, T_U16, T_S16, T_CU8, T_CS8, T_CU16, T_CS16 = 1, 2, 3, 4, 7, 8, 9, 10
+
+
+def _w(a, dt):
+    """two's-complement narrowing like the reference's implicit conversions"""
+    return np.asarray(a).astype(np.int64).astype({8: np.int8, 16: np.int16}[dt])
+
+
+def _cplx(re):
+    out = np.zeros((re.shape[0], 2), dtype=re.dtype); out[:, 0] = re
+    return out.reshape(-1)
+
+
+_CASTS = {
+    # AutoCast<int8_t>
+    (T_U8, T_S8): lambda b: _w(b.view(np.uint8).astype(np.int64) - 127, 8),                            # _uint8_int8, :137-144
+    (T_U16, T_S8): lambda b: _w((b.view(np.uint16).astype(np.int64) >> 8) - 127, 8),                   # _uint16_int8
+    (T_S16, T_S8): lambda b: _w(b.view(np.int16).astype(np.int64) >> 8, 8),                            # _int16_int8
+    # AutoCast<complex<int8_t>>
+    (T_U8, T_CS8): lambda b: _cplx(_w(b.view(np.uint8).astype(np.int64) - 127, 8)),                    # _uint8_cint8
+    (T_S8, T_CS8): lambda b: _cplx(b.view(np.int8).copy()),                                            # _int8_cint8
+    (T_U16, T_CS8): lambda b: _cplx(_w((b.view(np.int16).astype(np.int64) >> 8) - 65535, 8)),          # _uint16_cint8: read as int16, - ((2<<15)-1)
+    (T_S16, T_CS8): lambda b: _cplx(_w(b.view(np.int16).astype(np.int64) >> 8, 8)),                    # _int16_cint8
+    # AutoCast<int16_t>
+    (T_U8, T_S16): lambda b: _w((b.view(np.int8).astype(np.int64) - 127) << 8, 16),                    # _uint8_int16: read through int8_t*
+    (T_S8, T_S16): lambda b: _w(b.view(np.int8).astype(np.int64) << 8, 16),                            # _int8_int16
+    (T_U16, T_S16): lambda b: _w(b.view(np.uint16).astype(np.int64) - 65535, 16),                      # _uint16_int16: - ((2<<15)-1)
+    # AutoCast<complex<int16_t>>
+    (T_U8, T_CS16): lambda b: _cplx(_w((b.view(np.uint8).astype(np.int64) - 127) << 8, 16)),           # _uint8_cint16 (uint8 here)
+    (T_S8, T_CS16): lambda b: _cplx(_w(b.view(np.int8).astype(np.int64) * 256, 16)),                   # _int8_cint16
+    (T_U16, T_CS16): lambda b: _cplx(_w(b.view(np.uint16).astype(np.int64) - 32768, 16)),              # _uint16_cint16: - (1<<15)
+    (T_S16, T_CS16): lambda b: _cplx(b.view(np.int16).copy()),                                         # _int16_cint16
+}
+# complex sources reuse the scalar casts on the interleaved components (autocast.hh:44-68)
+_CASTS[(T_CU8, T_CS8)] = _CASTS[(T_U8, T_S8)]
+_CASTS[(T_CU16, T_CS8)] = _CASTS[(T_U16, T_S8)]
+_CASTS[(T_CS16, T_CS8)] = _CASTS[(T_S16, T_S8)]
+_CASTS[(T_CU8, T_CS16)] = _CASTS[(T_U8, T_S16)]
+_CASTS[(T_CS8, T_CS16)] = _CASTS[(T_S8, T_S16)]
+_CASTS[(T_CU16, T_CS16)] = _CASTS[(T_U16, T_S16)]
+for _t in (T_S8, T_CS8, T_S16, T_CS16):
+    _CASTS[(_t, _t)] = lambda b: b.copy()                                                              # _identity
+
+
+def autocast_supported(in_type, out_type):
+    return (int(in_type), int(out_type)) in _CASTS
+
+
+def autocast(raw_bytes, in_type, out_type):
+    """AutoCast<out_type> applied to a byte string holding elements of in_type; returns the output BYTES (uint8)."""
+    b = np.ascontiguousarray(raw_bytes).view(np.uint8).reshape(-1)
+    return np.ascontiguousarray(_CASTS[(int(in_type), int(out_type))](b)).view(np.uint8).reshape(-1)
+
+
 class FMDeemph:
     def __init__(self, sample_rate):
         self.alpha = int(_lib.orc_fmdeemph_alpha(float(sample_rate)))

@@ -334,6 +334,45 @@ static int run_cast(char **a) {
   return 0;
 }
 
+// AutoCast<Out> fed raw buffers of an arbitrary source type (src/autocast.hh:30-69: the whole cast table).
+// args: in_type_id out_type_id in.bin buffer_bytes prefix  ->  prefix.out (bytes), exit 4 when the reference refuses the pair
+class RawFeed : public Source {
+public:
+  void setup(Config::Type t, double Fs, size_t bs) { setConfig(Config(t, Fs, bs, 1)); }
+  void push(const RawBuffer &b) { send(b, false); }
+};
+template <class Out>
+static int run_castx_t(Config::Type in_type, size_t in_elem, char **a) {
+  std::vector<char> raw = slurp(a[0]);
+  size_t bytes_per_buf = strtoull(a[1], 0, 10);
+  std::string prefix = a[2];
+  RawFeed feed; AutoCast<Out> cast; RawDump dump;
+  feed.connect(&cast, true); cast.connect(&dump, true);
+  try { feed.setup(in_type, 1e6, bytes_per_buf / in_elem); }
+  catch (ConfigError &e) { return 4; }
+  dump.f = wopen(prefix + ".out");
+  RawBuffer work(bytes_per_buf);
+  for (size_t off = 0; off < raw.size(); off += bytes_per_buf) {
+    size_t n = std::min(bytes_per_buf, raw.size() - off);
+    memcpy(work.data(), raw.data() + off, n);
+    feed.push(RawBuffer(work, 0, n));
+  }
+  fclose(dump.f);
+  return 0;
+}
+static int run_castx(char **a) {
+  const int in_t = atoi(a[0]), out_t = atoi(a[1]);
+  static const size_t elem[] = {0, 1, 1, 2, 2, 4, 8, 2, 2, 4, 4, 8, 16};
+  if (in_t < 1 || in_t > 12) return 2;
+  switch (out_t) {
+    case Config::Type_s8: return run_castx_t<int8_t>((Config::Type)in_t, elem[in_t], a + 2);
+    case Config::Type_cs8: return run_castx_t< std::complex<int8_t> >((Config::Type)in_t, elem[in_t], a + 2);
+    case Config::Type_s16: return run_castx_t<int16_t>((Config::Type)in_t, elem[in_t], a + 2);
+    case Config::Type_cs16: return run_castx_t< std::complex<int16_t> >((Config::Type)in_t, elem[in_t], a + 2);
+  }
+  return 2;
+}
+
 static int run_deemph(char **a) {
   std::vector<char> raw = slurp(a[0]);
   size_t bs = strtoull(a[1], 0, 10);
@@ -434,6 +473,8 @@ int main(int argc, char **argv) {
     } else if (cmd == "cast" && argc == 6) {
       if (!strcmp(argv[2], "cu8")) return run_cast< std::complex<uint8_t> >(argv + 3);
       if (!strcmp(argv[2], "cs8")) return run_cast< std::complex<int8_t> >(argv + 3);
+    } else if (cmd == "castx" && argc == 7) {
+      return run_castx(argv + 2);
     } else if (cmd == "deemph" && argc == 6) {
       return run_deemph(argv + 2);
     } else if (cmd == "time" && argc == 14) {

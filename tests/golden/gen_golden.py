@@ -53,9 +53,38 @@ def run(args):
     subprocess.run([HARNESS] + [str(a) for a in args], check=True)
 
 
+def gen_cast_table(td):
+    """The whole AutoCast table (src/autocast.hh:30-69) run by the reference on one random byte string: for every
+    (source type, AutoCast<Out>) pair either the produced bytes or the fact that the reference refuses the pair."""
+    g = np.random.Generator(np.random.MT19937(0xCA57))
+    x = g.integers(0, 256, size=4096).astype(np.uint8)
+    x[:16] = [0, 1, 126, 127, 128, 129, 254, 255, 0, 255, 255, 0, 127, 127, 128, 128]     # the edges of every width
+    inp = os.path.join(td, "cast_in.bin"); x.tofile(inp)
+    out = {"x": x, "buffer_bytes": 1024}
+    refused = []
+    for out_t in (2, 8, 4, 10):
+        for in_t in range(1, 13):
+            pre = os.path.join(td, "cast_%d_%d" % (in_t, out_t))
+            r = subprocess.run([HARNESS, "castx", str(in_t), str(out_t), inp, "1024", pre])
+            if r.returncode == 0:
+                out["y_%d_%d" % (in_t, out_t)] = np.fromfile(pre + ".out", dtype=np.uint8)
+            elif r.returncode == 4:
+                refused.append((in_t, out_t))
+            else:
+                raise RuntimeError("harness failed on cast %d -> %d" % (in_t, out_t))
+    out["refused"] = np.array(refused, dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "cast_table.npz"), **out)
+    print("cast_table: %d casts, %d refused pairs" % (len([k for k in out if k.startswith("y_")]), len(refused)))
+
+
 def main():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    if "--cast-only" in sys.argv:
+        with tempfile.TemporaryDirectory() as td:
+            gen_cast_table(td)
+        return
     with tempfile.TemporaryDirectory() as td:
+        gen_cast_table(td)
         for (name, sc, Fs, Fc, Ff, width, order, ss, oFs, setcf, bs, N, amp, noise) in BB_CASES:
             dt = np.int16 if sc == "s16" else np.int8
             x = synth.iq_int(N, Fs, T3(amp), noise, 0x5D120000 + len(name), dt)

@@ -31,7 +31,63 @@ def test_fft_plan_errors():
     with pytest.raises(ConfigError):
         FFTPlan(0, FFTPlan.FORWARD)             # empty buffer (fftplan_fftw3.hh:93-97)
     with pytest.raises(ConfigError):
-        FFTPlan(96, FFTPlan.FORWARD)            # documented restriction of the device plan
+        FFTPlan((1 << 24) + 1, FFTPlan.FORWARD)  # documented upper limit of the device plan
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 6, 7, 12, 96, 100, 127, 1000, 1023, 4095, 4097, 5000, 10000, 44100, 100003,
+                               16384, 32768, 65536, 1 << 18, 1 << 20])
+def test_fft_plan_any_size(n):
+    """FFTPlan<float> accepts any size like the reference's FFTW plan (fftplan_fftw3.hh:83-106): powers of two above 8192
+    run the four-step decomposition, everything else Bluestein's convolution on the power-of-two engine."""
+    rng = np.random.default_rng(n)
+    batch = 3 if n <= 65536 else 2
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    fwd, bwd = FFTPlan(n, FFTPlan.FORWARD), FFTPlan(n, FFTPlan.BACKWARD)
+    X = fwd(x)
+    ref = np.fft.fft(x.astype(np.complex128), axis=1)
+    assert rel_rms(X, ref) < 5e-6, rel_rms(X, ref)
+    y = bwd(X)
+    assert rel_rms(y, x.astype(np.complex128) * n) < 1e-5
+    assert rel_rms(bwd(x), np.fft.ifft(x.astype(np.complex128), axis=1) * n) < 5e-6
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 100, 1024, 4097, 65536, 100003])
+def test_fft_plan_double(n):
+    """FFTPlan<double> (fftplan_fftw3.hh:12-75): double arithmetic on the device."""
+    from libsdr_b200.nodes import FFTPlan64
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    X = FFTPlan64(n, FFTPlan64.FORWARD)(x)
+    assert rel_rms(X, np.fft.fft(x, axis=1)) < 1e-12
+    assert rel_rms(FFTPlan64(n, FFTPlan64.BACKWARD)(X), x * n) < 1e-12
+    with pytest.raises(ConfigError):
+        FFTPlan64(0, 0)
+
+
+@pytest.mark.parametrize("block", [1000, 3000, 4095, 5000, 8192, 16384, 20000])
+def test_filter_any_block_size(block):
+    """FilterNode(block) for blocks that are not a power of two or exceed 4096 (filternode.hh:236 takes any): same taps,
+    same normalisation, same causal convolution -- checked against the time-domain identity and, where
+    its O(n^2) DFT is affordable, the oracle's restatement of FilterSink/FilterSource."""
+    Fs = 2.4e6
+    nblk = 5
+    x = synth.iq_f32(nblk * block + 777, Fs, [(0.5, 150e3, 0.0), (0.3, -400e3, 1.0), (0.2, 900e3, 2.0)], 0.01, block).view(np.complex64).reshape(-1)
+    f = FilterNode(block)
+    f.addFilter(100e3, 200e3); f.addFilter(-500e3, -300e3)
+    f.config(sample_rate=Fs, buffer_size=block)
+    taps = f.design(0)[1] if block <= 8192 else None
+    y1 = f.process(x[:2 * block + 100]); y2 = f.process(x[2 * block + 100:])        # ragged: the remainder waits for the next call
+    y = np.concatenate([y1, y2], axis=1)
+    assert y.shape == (2, nblk * block)
+    for k, (lo, hi) in enumerate([(100e3, 200e3), (-500e3, -300e3)]):
+        t = orc.filter_taps(block, lo, hi, Fs)
+        if k == 0 and taps is not None:
+            np.testing.assert_array_equal(taps, t)
+        ref = orc.filter_timedomain_f64(t, x[:nblk * block])
+        assert rel_rms(y[k], ref) < TOL, (block, k, rel_rms(y[k], ref))
+    if block <= 3000:      # the oracle's own OLA (any size through its O(n^2) DFT) agrees as well
+        o = orc.FilterOLA(block, 100e3, 200e3, Fs)
+        assert rel_rms(y[0], o.process(x[:nblk * block])) < TOL
 
 
 def test_fft_device_pointers():
@@ -125,6 +181,6 @@ def test_filter_config_errors():
         f.config(Config(_lib.T_CS16, 1e6, 1024, 1))
     assert f.config(Config(_lib.T_CF32, 0.0, 1024, 1)).type == _lib.T_UNDEFINED
     with pytest.raises(ConfigError):
-        FilterNode(1000)
+        FilterNode((1 << 22) + 1)
     with pytest.raises(RuntimeError):
         FilterNode(64).process(np.zeros(64, dtype=np.complex64))

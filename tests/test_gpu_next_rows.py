@@ -129,3 +129,26 @@ def test_real_baseband_frequency_setter_and_fm_chain():
     fm, ofm = FMDemod("s16"), orc.FMDemod(orc.S16)
     fm.config(Config(_lib.T_CS16, Fs / ss, n // ss, 1))
     np.testing.assert_array_equal(fm.process(y)[1:], ofm.process(yo)[1:])
+
+
+def test_autocast_whole_table():
+    """Every cast of src/autocast.hh:30-69 on the device == the reference's bytes (golden) == the oracle; refused pairs
+    raise ConfigError with the reference's message; host and device entry points."""
+    import torch
+    from conftest import load_golden
+    from libsdr_b200.nodes import autocast
+    g = load_golden("cast_table")
+    x = g["x"]
+    xd = torch.from_numpy(x).cuda()
+    for k in g.files:
+        if not k.startswith("y_"):
+            continue
+        _, i, o = k.split("_")
+        np.testing.assert_array_equal(autocast(x, int(i), int(o)), g[k], err_msg=k)
+        np.testing.assert_array_equal(autocast(xd, int(i), int(o)).cpu().numpy(), g[k], err_msg=k + " (device)")
+    for i, o in g["refused"]:
+        with pytest.raises(ConfigError, match="AutoCast: Can not cast"):
+            autocast(x, int(i), int(o))
+    big = np.random.default_rng(3).integers(0, 256, size=1 << 20).astype(np.uint8)
+    for i, o in ((3, 10), (1, 8), (9, 8), (4, 2)):
+        np.testing.assert_array_equal(autocast(big, i, o), orc.autocast(big, i, o))

@@ -138,3 +138,20 @@ def test_real_baseband_matches_reference(name):
     outs = [o.process(g["x"][k:k + bs]) for k in range(0, g["x"].shape[0], bs)]
     np.testing.assert_array_equal(np.array([y.shape[0] for y in outs], dtype=np.uint32), g["counts"])
     np.testing.assert_array_equal(np.concatenate(outs), g["bb"])
+
+
+def test_autocast_table_oracle_reproduces_reference():
+    """oracle.autocast (numpy) == the reference's AutoCast<Scalar> on every pair of its table; pairs the reference
+    refuses are refused (tests/golden/cast_table.npz, generated by gen_golden.py from the live reference)."""
+    g = load_golden("cast_table")
+    n = 0
+    for k in g.files:
+        if not k.startswith("y_"):
+            continue
+        _, i, o = k.split("_")
+        assert orc.autocast_supported(int(i), int(o))
+        np.testing.assert_array_equal(orc.autocast(g["x"], int(i), int(o)), g[k], err_msg=k)
+        n += 1
+    assert n == 24 and len(g["refused"]) == 24
+    for i, o in g["refused"]:
+        assert not orc.autocast_supported(int(i), int(o))
