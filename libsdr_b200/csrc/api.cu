@@ -158,7 +158,7 @@ size_t audio_bytes(int scalar, int demod) {
   return scalar_bytes(scalar);
 }
 
-size_t in_sample_bytes(const sdrg_iqbb *h) { return h->in_fmt ? 2 : sample_bytes(h->d.scalar); }
+size_t in_sample_bytes(const sdrg_iqbb *h) { return h->in_fmt == 5 ? 1 : (h->in_fmt ? 2 : sample_bytes(h->d.scalar)); }
 int input_type_of(const sdrg_iqbb *h) {
   if (h->real_input) return h->d.scalar;
   return h->in_fmt == 2 ? SDRG_T_CU8 : (h->in_fmt == 3 ? SDRG_T_CS8 : complex_type_of(h->d.scalar));
@@ -309,6 +309,9 @@ int design_only(sdrg_iqbb *h) {
   }
   if (d.sub_sample < 1) d.sub_sample = 1;    // the reference would divide by zero
   if (d.sub_sample > (1u << 30)) return set_error(SDRG_ERR_CONFIG, "%s: sub-sampling %zu too large", node_name(h), d.sub_sample);
+  if (h->real_input && d.scalar == SDRG_T_S8 && (short)((int)(short)d.sub_sample * (int)(short)d.sub_sample) == 0)
+    return set_error(SDRG_ERR_CONFIG, "BaseBand<int8_t>: sub-sampling %zu makes int16(ss*ss) zero -- the reference divides by zero "
+                     "(complex<int16_t>::operator/=, src/baseband.hh:434)", d.sub_sample);
   design_filter(h);
   h->nco_Fs = h->real_input ? h->r_Fs : double(d.Fs);       // BaseBand keeps the double rate (baseband.hh:371)
   design_lut_increment(d, h->nco_Fs);
@@ -356,13 +359,14 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
   a.neg = h->d.negative ? 1u : 0u;
   a.zero_next = h->acc_dirty[q];
   a.in_fmt = (uint32_t)h->in_fmt;
-  a.fir_shift = h->real_input ? 16u : 14u;
+  a.fir_shift = h->real_input ? (h->d.scalar == SDRG_T_S8 ? 8u : 16u) : 14u;     // BaseBand: >> Traits<Scalar>::shift
   IqbbFinalizeArgs f{};
   f.acc_cur = h->d_acc[p]; f.acc_next = h->d_acc[q];
   f.bb_out = d_bb; f.audio_out = d_audio;
   f.fm_last_in = fm_last_in; f.fm_last_out = fm_last_out;
   f.n_out = (uint32_t)adv.n_out; f.ss = a.ss; f.demod = (uint32_t)demod; f.e0 = adv.e0;
   f.seg = seg; f.in_place = (uint32_t)in_place;
+  f.narrow16 = (h->real_input && h->d.scalar == SDRG_T_S8) ? 1u : 0u;
   if (h->fold) {
     IqbbFoldArgs fa{};
     fa.x = d_in; fa.acc_cur = a.acc_cur; fa.acc_next = a.acc_next;
@@ -686,18 +690,18 @@ int sdrg_iqbb_create(int scalar, double Fc, double Ff, double width, size_t orde
   return SDRG_OK;
 }
 
-// BaseBand<Scalar>(Fc, Ff, width, order, sub_sample) on a REAL stream (src/baseband.hh:339-350).  Only
-// int16_t is built (the reference instantiates it nowhere else either: examples/, cmd/ use int16 audio).
+// BaseBand<Scalar>(Fc, Ff, width, order, sub_sample) on a REAL stream (src/baseband.hh:339-350), Scalar = int16_t or
+// int8_t.  The int8 instantiation computes in 16 bits throughout (see iqbb_finalize.cuh::fin_value_s8_real).
 int sdrg_iqbb_create_real(int scalar, double Fc, double Ff, double width, size_t order, size_t sub_sample,
                           sdrg_iqbb **out) {
   if (!out) return set_error(SDRG_ERR_ARG, "null argument");
   *out = nullptr;
-  if (scalar != SDRG_T_S16)
-    return set_error(SDRG_ERR_ARG, "BaseBand: unsupported scalar type %s (%d), only int16", type_name(scalar), scalar);
-  int rc = sdrg_iqbb_create(SDRG_T_S16, Fc, Ff, width, order, sub_sample, 0.0, out);
+  if (scalar != SDRG_T_S16 && scalar != SDRG_T_S8)
+    return set_error(SDRG_ERR_ARG, "BaseBand: unsupported scalar type %s (%d), only int16 and int8", type_name(scalar), scalar);
+  int rc = sdrg_iqbb_create(scalar, Fc, Ff, width, order, sub_sample, 0.0, out);
   if (rc) return rc;
   sdrg_iqbb *h = *out;
-  h->real_input = true; h->in_fmt = 4;
+  h->real_input = true; h->in_fmt = scalar == SDRG_T_S8 ? 5 : 4;
   h->r_Ff = Ff; h->r_width = width;
   return SDRG_OK;
 }

@@ -49,6 +49,23 @@ template <> struct Fin<SDRG_T_F32> {
   static __device__ __forceinline__ Au usb(float2 v) { return (v.x + v.y) / 2; }
 };
 
+// BaseBand<int8_t> (src/baseband.hh:304-529 with Scalar = int8_t): `_last` is complex<int16_t> and
+// out = _last / complex<int16_t>(ss) is libstdc++'s complex<int16_t>::operator/=, whose real part is narrowed to
+// int16 BEFORE the division (`const _Tp __r = ...`) while the imaginary part divides the int product; n = int16(ss ss).
+__device__ __forceinline__ int2 fin_value_s8_real(const int2 s, uint32_t ss) {
+  const int z = (int)(short)ss, nn = (int)(short)(z * z);
+  if (nn == 0) return make_int2(0, 0);                          // refused at config(): the reference divides by zero
+  const int sr = (int)(short)s.x, si = (int)(short)s.y;
+  const int re = (int)(short)(((int)(short)(sr * z)) / nn);
+  const int im = (int)(short)((si * z) / nn);
+  return make_int2((int)(signed char)re, (int)(signed char)im);
+}
+template <int SCALAR>
+__device__ __forceinline__ auto fin_value(const typename Fin<SCALAR>::Acc s, const IqbbFinalizeArgs &a) {
+  if constexpr (SCALAR == SDRG_T_S8) { if (a.narrow16) return fin_value_s8_real(s, a.ss); }
+  return Fin<SCALAR>::value(s, a.ss);
+}
+
 // is output j the first element of its segment (= of the buffer it is delivered with)?
 // e = call-relative index of the sample that completes window j (< n <= 2^30, so 32-bit); the
 // previous completion e - ss lies in an earlier buffer iff (e mod seg) < ss.
@@ -77,13 +94,13 @@ __device__ __forceinline__ void iqbb_finalize_block(const IqbbFinalizeArgs &a, c
     if (fm) {     // carried FM angle: the last sample of this call that contributes
       typename F::Last last = *(const typename F::Last *)a.fm_last_in;
       for (int64_t k = (int64_t)a.n_out - 1; k >= 0; --k) {
-        if (!seg_first((uint32_t)k, a)) { last = F::phi(F::value(acc[k], a.ss)); break; }
+        if (!seg_first((uint32_t)k, a)) { last = F::phi(fin_value<SCALAR>(acc[k], a)); break; }
       }
       *(typename F::Last *)a.fm_last_out = last;
     }
   }
   const bool valid = j < a.n_out;
-  auto v = F::value(valid ? acc[j] : typename F::Acc(), a.ss);
+  auto v = fin_value<SCALAR>(valid ? acc[j] : typename F::Acc(), a);
   if (valid && a.bb_out) ((typename F::Bb *)a.bb_out)[j] = F::store(v);
   if (!a.audio_out) return;                      // uniform
   if (a.demod == SDRG_DEMOD_AM) { if (valid) ((typename F::Au *)a.audio_out)[j] = F::am(v); return; }
@@ -101,7 +118,7 @@ __device__ __forceinline__ void iqbb_finalize_block(const IqbbFinalizeArgs &a, c
   else {
     int64_t k = (int64_t)j - 1;
     while (k >= 0 && seg_first((uint32_t)k, a)) --k;
-    last = (k >= 0) ? F::phi(F::value(acc[k], a.ss)) : *(const typename F::Last *)a.fm_last_in;
+    last = (k >= 0) ? F::phi(fin_value<SCALAR>(acc[k], a)) : *(const typename F::Last *)a.fm_last_in;
   }
   out[j] = F::fm(last, p);
 }

@@ -36,7 +36,11 @@ __device__ __forceinline__ void prologue(const IqbbAccumArgs &a) {
   }
   if (blockIdx.x == 0) {
     const int64_t H = a.hist_len, n = a.n;
-    if (sizeof(Sample) == 4 && a.in_fmt != 0) {          // fused AutoCast: the history holds raw 8-bit pairs
+    if (a.in_fmt == 5) {                                 // real int8 stream: one byte per sample
+      const signed char *x = (const signed char *)a.x, *hi = (const signed char *)a.hist_in;
+      signed char *ho = (signed char *)a.hist_out;
+      for (int64_t k = threadIdx.x; k < H; k += blockDim.x) { const int64_t i = n - H + k; ho[k] = (i >= 0) ? x[i] : hi[H + i]; }
+    } else if (sizeof(Sample) == 4 && a.in_fmt != 0) {   // fused AutoCast: the history holds raw 8-bit pairs
       const char2 *x = (const char2 *)a.x, *hi = (const char2 *)a.hist_in;
       char2 *ho = (char2 *)a.hist_out;
       for (int64_t k = threadIdx.x; k < H; k += blockDim.x) { const int64_t i = n - H + k; ho[k] = (i >= 0) ? x[i] : hi[H + i]; }

@@ -110,7 +110,12 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs 
   for (int k = tid; k < n_xs; k += kT) {
     const int64_t i = tile_base - H + k;
     uint32_t v = 0;
-    if (IS_S8) {
+    if (IS_S8 && a.in_fmt == 5) {                                // BaseBand<int8_t>: real samples, (x, 0)
+      signed char s = 0;
+      if (i < 0) s = ((const signed char *)a.hist_in)[H + i];
+      else if (i < (int64_t)a.n) s = ((const signed char *)a.x)[i];
+      v = (uint32_t)(uint16_t)(int16_t)s;
+    } else if (IS_S8) {
       char2 s = make_char2(0, 0);
       if (i < 0) s = ((const char2 *)a.hist_in)[H + i];
       else if (i < (int64_t)a.n) s = ((const char2 *)a.x)[i];
@@ -156,8 +161,14 @@ __global__ void __launch_bounds__(kT) iqbb_accum_int_kernel(const IqbbAccumArgs 
   const uint32_t i0 = (uint32_t)tile_base + (uint32_t)ob;
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
-    int yr = ((int)(A1[r] - A3[r])) >> a.fir_shift;
-    int yi = ((int)(A1[r] + A2[r])) >> a.fir_shift;
+    int yr, yi;
+    if (IS_S8 && a.in_fmt == 5) {     // BaseBand<int8_t>: `res` is complex<int16_t>, the sum wraps at 16 bits, then >> 8
+      yr = ((int)(short)(A1[r] - A3[r])) >> a.fir_shift;
+      yi = ((int)(short)(A1[r] + A2[r])) >> a.fir_shift;
+    } else {
+      yr = ((int)(A1[r] - A3[r])) >> a.fir_shift;
+      yi = ((int)(A1[r] + A2[r])) >> a.fir_shift;
+    }
     if (IS_S8) { yr = (int)(short)yr; yi = (int)(short)yi; }   // narrowed to complex<int16_t> on the call
     if (a.nco) {
       const uint32_t ph = (a.phase0 + (i0 + r) * a.inc) & 0x7fffu;
@@ -464,7 +475,7 @@ size_t accum_smem_f32(uint32_t Lp, uint32_t H) {
 int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st) {
   if (a.n == 0) return SDRG_OK;
   const unsigned grid = (unsigned)((a.n + kTile - 1) / kTile);
-  if (scalar != SDRG_T_F32 && a.host_taps && a.taps_len <= 32) {
+  if (scalar != SDRG_T_F32 && a.host_taps && a.taps_len <= 32 && a.in_fmt != 5) {     // (BaseBand<int8_t> stays on the generic kernel)
     // zero taps in FRONT up to the next even count: x[n-(LP-1)+t] k'[t] with k'[t] = 0 for t < pad
     const int lp = (int)((a.taps_len + 1) & ~1u), pad = lp - (int)a.taps_len;
     IqbbTaps taps;

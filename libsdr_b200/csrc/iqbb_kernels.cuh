@@ -31,7 +31,8 @@ struct IqbbAccumArgs {
   uint32_t    neg;        // negative frequency shift: idx = 127 - idx
   uint32_t    zero_next;
   uint32_t    in_fmt;     // int16 path only: 0 = complex<int16_t> input, 2 = complex uint8, 3 = complex int8 (fused AutoCast),
-                          // 4 = REAL int16 (BaseBand<int16_t>, src/baseband.hh:304): sample = (x, 0)
+                          // 4 = REAL int16 (BaseBand<int16_t>, src/baseband.hh:304): sample = (x, 0);
+                          // int8 path: 5 = REAL int8 (BaseBand<int8_t>): sample = (x, 0), FIR sum wrapped to 16 bits before the shift
   uint32_t    fir_shift;  // integer paths: the FIR result is shifted right by this (14 IQBaseBand, 16 BaseBand)
   uint32_t    div_m, div_s; // per-warp kernel: q / ss == (q * div_m) >> div_s for q < 2^31 (filled in by its launcher)
   uint32_t    zero;       // always 0: a third addend that keeps the kernel's plain additions on the ALU pipe (IADD3) --
@@ -84,6 +85,7 @@ struct IqbbFinalizeArgs {
   uint32_t    e0;         // call-relative index of the sample that completes slot 0
   uint64_t    seg;        // buffer_size (segment length in input samples); 0 = one segment
   uint32_t    in_place;   // FM: what element 0 of every segment shows
+  uint32_t    narrow16;   // BaseBand<int8_t>: the window sum and the division run in int16 (complex<int16_t>::operator/=)
 };
 
 // One process() call of a channel bank (bank_kernels.cu); window geometry as in IqbbAccumArgs

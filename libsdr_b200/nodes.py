@@ -164,16 +164,17 @@ class IQBaseBand:
 
 
 class BaseBand(IQBaseBand):
-    """BaseBand<int16_t>(Fc, Ff, width, order, sub_sample) on a REAL int16 stream (src/baseband.hh:304-529):
-    complex band-pass FIR (gain 2^16) -> NCO -> mean of exactly sub_sample samples; output (n, 2) int16.
+    """BaseBand<Scalar>(Fc, Ff, width, order, sub_sample) on a REAL stream (src/baseband.hh:304-529), Scalar = int16_t
+    (default) or int8_t: complex band-pass FIR (gain 2^16 resp. 2^8) -> NCO -> mean of exactly sub_sample samples;
+    output (n, 2) of the same scalar.  The int8 instantiation computes in 16 bits throughout, like the reference.
     The 4-argument reference constructor (Ff = Fc, baseband.hh:322) is `BaseBand(Fc, None, ...)`."""
 
     _in_shape = (-1,)
 
-    def __init__(self, Fc, Ff, width, order, sub_sample):
-        self.scalar = _lib.T_S16
-        self.dtype = np.int16
-        self._in_type = _lib.T_S16
+    def __init__(self, Fc, Ff, width, order, sub_sample, scalar="s16"):
+        self.scalar = scalar_id(scalar)
+        self.dtype = _NP[self.scalar]
+        self._in_type = self.scalar
         self._h = C.c_void_p()
         if Ff is None:
             Ff = Fc

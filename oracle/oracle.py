@@ -144,22 +144,29 @@ _lib.orc_rbb_config.restype = C.c_int
 _lib.orc_rbb_set_frequency_shift.argtypes = [C.POINTER(_IQBB), C.c_double]
 _lib.orc_rbb_process.argtypes = [C.POINTER(_IQBB), C.c_void_p, C.c_size_t, C.c_void_p]
 _lib.orc_rbb_process.restype = C.c_size_t
+_lib.orc_rbb_init8.argtypes = [C.POINTER(_IQBB), C.c_double, C.c_double, C.c_double, C.c_size_t, C.c_size_t]
+_lib.orc_rbb_process8.argtypes = [C.POINTER(_IQBB), C.c_void_p, C.c_size_t, C.c_void_p]
+_lib.orc_rbb_process8.restype = C.c_size_t
 
 
 class BaseBand:
-    """Oracle real-input BaseBand<int16_t> (src/baseband.hh:304-529): real int16 in, (n,2) int16 out."""
+    """Oracle real-input BaseBand<Scalar> (src/baseband.hh:304-529): real int16 in, (n,2) int16 out; with
+    scalar=S8 the int8 instantiation (16-bit arithmetic throughout): real int8 in, (n,2) int8 out."""
 
-    def __init__(self, Fc, Ff, width, order, sub_sample):
+    def __init__(self, Fc, Ff, width, order, sub_sample, scalar=S16):
         self.s = _IQBB()
-        _lib.orc_rbb_init(C.byref(self.s), Fc, Ff, width, order, sub_sample)
+        self.scalar = scalar
+        (_lib.orc_rbb_init8 if scalar == S8 else _lib.orc_rbb_init)(C.byref(self.s), Fc, Ff, width, order, sub_sample)
 
     def config(self, sample_rate, buffer_size):
         return _lib.orc_rbb_config(C.byref(self.s), sample_rate, buffer_size)
 
     def process(self, x):
-        x = np.ascontiguousarray(x, dtype=np.int16).reshape(-1)
-        out = np.zeros((x.shape[0] // max(1, self.s.sub_sample) + 2, 2), dtype=np.int16)
-        n = _lib.orc_rbb_process(C.byref(self.s), _p(x), x.shape[0], _p(out))
+        dt = np.int8 if self.scalar == S8 else np.int16
+        x = np.ascontiguousarray(x, dtype=dt).reshape(-1)
+        out = np.zeros((x.shape[0] // max(1, self.s.sub_sample) + 2, 2), dtype=dt)
+        fn = _lib.orc_rbb_process8 if self.scalar == S8 else _lib.orc_rbb_process
+        n = fn(C.byref(self.s), _p(x), x.shape[0], _p(out))
         return out[:n].copy()
 
     def set_frequency_shift(self, Fc):

@@ -241,11 +241,11 @@ static int run_ola(char **a) {
   return 0;
 }
 
-struct RBB : public BaseBand<int16_t> {
-  RBB(double Fc, double Ff, double w, size_t o, size_t ss) : BaseBand<int16_t>(Fc, Ff, w, o, ss) {}
+template <class S> struct RBB : public BaseBand<S> {
+  RBB(double Fc, double Ff, double w, size_t o, size_t ss) : BaseBand<S>(Fc, Ff, w, o, ss) {}
   void dump(FILE *f) {
-    int64_t hdr[4] = { (int64_t)this->_order, (int64_t)this->_sub_sample, (int64_t)FreqShiftBase<int16_t>::_lut_inc,
-                       (int64_t)(0 > FreqShiftBase<int16_t>::_freq_shift) };
+    int64_t hdr[4] = { (int64_t)this->_order, (int64_t)this->_sub_sample, (int64_t)FreqShiftBase<S>::_lut_inc,
+                       (int64_t)(0 > FreqShiftBase<S>::_freq_shift) };
     fwrite(hdr, sizeof(hdr), 1, f);
     for (size_t i = 0; i < this->_order; i++) {
       int32_t v[2] = { this->_kernel[i].real(), this->_kernel[i].imag() }; fwrite(v, sizeof(v), 1, f);
@@ -253,22 +253,23 @@ struct RBB : public BaseBand<int16_t> {
   }
 };
 
+template <class S>
 static int run_rbb(char **a) {
   std::vector<char> raw = slurp(a[0]);
   size_t bs = strtoull(a[1], 0, 10);
   double Fs = atof(a[2]), Fc = atof(a[3]), Ff = atof(a[4]), width = atof(a[5]);
   size_t order = strtoull(a[6], 0, 10), ss = strtoull(a[7], 0, 10);
   std::string prefix = a[8];
-  size_t total = raw.size() / sizeof(int16_t);
-  Feed<int16_t> feed; RBB bb(Fc, Ff, width, order, ss); Dump< std::complex<int16_t> > dump;
+  size_t total = raw.size() / sizeof(S);
+  Feed<S> feed; RBB<S> bb(Fc, Ff, width, order, ss); Dump< std::complex<S> > dump;
   dump.f = wopen(prefix + ".bb");
   feed.connect(&bb, true); bb.connect(&dump, true);
   feed.setup(Fs, bs);
   FILE *fp = wopen(prefix + ".params"); bb.dump(fp); fclose(fp);
-  Buffer<int16_t> work(bs);
+  Buffer<S> work(bs);
   for (size_t off = 0; off < total; off += bs) {
     size_t n = std::min(bs, total - off);
-    memcpy(work.data(), raw.data() + off * sizeof(int16_t), n * sizeof(int16_t));
+    memcpy(work.data(), raw.data() + off * sizeof(S), n * sizeof(S));
     feed.push(work.head(n), false);
   }
   fclose(dump.f);
@@ -463,7 +464,9 @@ int main(int argc, char **argv) {
     } else if (cmd == "ola" && argc == 8) {
       return run_ola(argv + 2);
     } else if (cmd == "rbb" && argc == 11) {
-      return run_rbb(argv + 2);
+      return run_rbb<int16_t>(argv + 2);
+    } else if (cmd == "rbb8" && argc == 11) {
+      return run_rbb<int8_t>(argv + 2);
     } else if (cmd == "wav" && argc == 8) {
       std::string t = argv[2];
       if (t == "u8") return run_wav<uint8_t>(argv + 3);

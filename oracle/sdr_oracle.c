@@ -278,14 +278,63 @@ int orc_rbb_config(orc_iqbb *s, double Fs, size_t buffer_size) {
       norm += hypot(re, im);
     }
     for (size_t i = 0; i < s->order; i++) {
-      s->kr[i] = (int32_t)(((double)(1 << 16) * ar[i]) / norm);
-      s->ki[i] = (int32_t)(((double)(1 << 16) * ai[i]) / norm);
+      const int sh = s->scalar == ORC_S8 ? 8 : 16;                /* 1 << Traits<Scalar>::shift */
+      s->kr[i] = (int32_t)(((double)(1 << sh) * ar[i]) / norm);
+      s->ki[i] = (int32_t)(((double)(1 << sh) * ai[i]) / norm);
     }
   }
   s->out_bs = buffer_size / s->sub_sample + ((buffer_size % s->sub_sample) ? 1 : 0);
   s->out_rate = Fs / (double)s->sub_sample;
   s->last_r = s->last_i = 0; s->sample_count = 0; s->ring_offset = 0;
   return 0;
+}
+
+/* BaseBand<int8_t>: the same class with Scalar = int8_t, i.e. SScalar = int16_t and CSScalar = complex<int16_t>
+ * (src/freqshift.hh:20-22).  Everything the int16 instantiation does in 32 bits happens in 16 here:
+ *   - the kernel is complex<int16_t>(2^8 alpha / norm), the FIR sum `res += _kernel[i] * _ring[idx]` wraps at 16 bits
+ *     on every step (complex<int16_t> * int16_t and += narrow back to int16_t), then >> 8 (baseband.hh:443-453);
+ *   - the mixer is FreqShiftBase<int8_t>'s (the int16 LUT, 16-bit product wrap: nco_s8 above);
+ *   - `_last` is complex<int16_t>: the window sum wraps at 16 bits;
+ *   - out = _last / CSScalar(sub_sample) is libstdc++'s complex<int16_t>::operator/=: the REAL part goes through
+ *     `const _Tp __r = re * z.re + im * z.im` (narrowed to int16 BEFORE the division) while the imaginary part is
+ *     (im * z.re - re * z.im) / n in int; n = std::norm(z) = int16(ss * ss); then narrowed to complex<int8_t>.
+ * scalar must be set to ORC_S8 between orc_rbb_init and orc_rbb_config (orc_rbb_init8 does). */
+void orc_rbb_init8(orc_iqbb *s, double Fc, double Ff, double width, size_t order, size_t sub_sample) {
+  orc_rbb_init(s, Fc, Ff, width, order, sub_sample);
+  s->scalar = ORC_S8;
+  build_lut(s);
+}
+size_t orc_rbb_process8(orc_iqbb *s, const int8_t *in, size_t n, int8_t *out) {
+  size_t j = 0;
+  const size_t L = s->order;
+  for (size_t i = 0; i < n; i++) {
+    s->ring_r[s->ring_offset] = in[i];
+    int16_t fr = 0, fi = 0;
+    size_t idx = s->ring_offset + 1;
+    if (L == idx) idx = 0;
+    for (size_t t = 0; t < L; t++, idx++) {
+      if (L == idx) idx = 0;
+      const int16_t x = (int16_t)s->ring_r[idx];
+      const int16_t pr = (int16_t)((int)(int16_t)s->kr[t] * (int)x), pi = (int16_t)((int)(int16_t)s->ki[t] * (int)x);
+      fr = (int16_t)(fr + pr); fi = (int16_t)(fi + pi);
+    }
+    int32_t vr = (int16_t)(fr >> 8), vi = (int16_t)(fi >> 8);     /* >> Traits<int8_t>::shift on complex<int16_t> */
+    nco_s8(s, &vr, &vi);
+    s->last_r = (int16_t)(s->last_r + vr); s->last_i = (int16_t)(s->last_i + vi);
+    s->sample_count++;
+    s->ring_offset++;
+    if (L == s->ring_offset) s->ring_offset = 0;
+    if (s->sub_sample == s->sample_count) {
+      const int16_t zr = (int16_t)s->sub_sample;                   /* CSScalar(_sub_sample) */
+      const int16_t nn = (int16_t)((int)zr * (int)zr);             /* std::norm, narrowed to _Tp */
+      const int16_t r = (int16_t)((int)(int16_t)s->last_r * (int)zr);
+      const int16_t re = (int16_t)((int)r / (int)nn);
+      const int16_t im = (int16_t)(((int)(int16_t)s->last_i * (int)zr) / (int)nn);
+      out[2 * j] = (int8_t)re; out[2 * j + 1] = (int8_t)im;
+      s->last_r = s->last_i = 0; s->sample_count = 0; j++;
+    }
+  }
+  return j;
 }
 
 /* FreqShiftBase::setFrequencyShift, src/freqshift.hh:62-65 */

@@ -90,6 +90,10 @@ void orc_rbb_init(orc_iqbb *s, double Fc, double Ff, double width, size_t order,
 int  orc_rbb_config(orc_iqbb *s, double sample_rate, size_t buffer_size);
 void orc_rbb_set_frequency_shift(orc_iqbb *s, double Fc);
 size_t orc_rbb_process(orc_iqbb *s, const int16_t *in, size_t n, int16_t *out_iq);
+/* BaseBand<int8_t>: 16-bit arithmetic throughout (see sdr_oracle.c); sub_sample values whose square is 0 mod 2^16
+ * divide by zero in the reference (SIGFPE) and must not be passed. */
+void orc_rbb_init8(orc_iqbb *s, double Fc, double Ff, double width, size_t order, size_t sub_sample);
+size_t orc_rbb_process8(orc_iqbb *s, const int8_t *in, size_t n, int8_t *out_iq);
 
 /* AutoCast< std::complex<int16_t> > from complex 8-bit input (src/autocast.hh:187-204): n BYTES in,
  * n int16 out.  cu8: the bytes are read through an int8_t pointer (reference quirk), (v-127)<<8;

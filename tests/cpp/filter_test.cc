@@ -67,7 +67,7 @@ int main() {
     CHECK(rel_rms(c1.data, ref1) < 1e-5); CHECK(rel_rms(c2.data, ref2) < 1e-5);
     work.unref();
   }
-  {   // FFTPlan<float>: forward then backward returns n * x; empty / odd sizes throw ConfigError
+  {   // FFTPlan<float>: forward then backward returns n * x; an empty buffer throws ConfigError
     const size_t n = 4096;
     Buffer<cf> a(n), b(n);
     for (size_t i = 0; i < n; i++) a[i] = x[i];
@@ -83,9 +83,25 @@ int main() {
     bool threw = false;
     try { Buffer<cf> e; FFTPlan<float> p(e, FFT::FORWARD); } catch (ConfigError &) { threw = true; }
     CHECK(threw);
-    threw = false;
-    try { Buffer<cf> o(96); FFTPlan<float> p(o, FFT::FORWARD); } catch (ConfigError &) { threw = true; }
-    CHECK(threw);
+    {   // any size, like the reference's FFTW plan: 96 points (Bluestein), forward then backward returns n * x
+      Buffer<cf> o(96), O(96), back(96);
+      for (size_t i = 0; i < 96; i++) o[i] = cf(float(i % 7) - 3.0f, float(i % 5) - 2.0f);
+      FFT::exec(o, O, FFT::FORWARD); FFT::exec(O, back, FFT::BACKWARD);
+      double err = 0, ref = 0;
+      for (size_t i = 0; i < 96; i++) { err += std::norm(std::complex<double>(back[i]) / 96.0 - std::complex<double>(o[i])); ref += std::norm(std::complex<double>(o[i])); }
+      CHECK(std::sqrt(err / ref) < 1e-5);
+      std::complex<double> dc(0, 0);
+      for (size_t i = 0; i < 96; i++) dc += std::complex<double>(o[i]);
+      CHECK(std::abs(std::complex<double>(O[0]) - dc) < 1e-3);
+    }
+    {   // FFTPlan<double>
+      Buffer< std::complex<double> > o(100), O(100);
+      for (size_t i = 0; i < 100; i++) o[i] = std::complex<double>(double(i % 9) - 4.0, double(i % 4) - 1.5);
+      FFT::exec(o, O, FFT::FORWARD);
+      std::complex<double> dc(0, 0), nyq(0, 0);
+      for (size_t i = 0; i < 100; i++) { dc += o[i]; nyq += (i % 2 ? -1.0 : 1.0) * o[i]; }
+      CHECK(std::abs(O[0] - dc) < 1e-9); CHECK(std::abs(O[50] - nyq) < 1e-9);
+    }
     a.unref(); b.unref();
   }
   std::printf(failures ? "filter_test: %d FAILED\n" : "filter_test: ok\n", failures);

@@ -77,14 +77,38 @@ def gen_cast_table(td):
     print("cast_table: %d casts, %d refused pairs" % (len([k for k in out if k.startswith("y_")]), len(refused)))
 
 
+def gen_rbb8(td):
+    """Real-input BaseBand<int8_t> (src/baseband.hh:304-529 with Scalar = int8_t: 16-bit arithmetic throughout)."""
+    for (name, Fs, Fc, Ff, width, order, ss, bs, N, amp) in [
+            ("rbb8_pos", 48000.0, 10e3, 10e3, 3e3, 21, 6, 1000, 9000, 60),
+            ("rbb8_neg_wrap", 2.4e6, -300.5e3, -280e3, 50e3, 32, 50, 4096, 30000, 127),     # full scale: every 16-bit wrap is exercised
+            ("rbb8_inc0_ss1", 8000.0, 0.0, 1e3, 500.0, 9, 1, 512, 3000, 100),
+            ("rbb8_ss200", 1e6, 123e3, 120e3, 20e3, 15, 200, 2048, 20000, 90)]:                 # ss^2 = 40000 wraps int16 in std::norm
+        t = np.arange(N) / Fs
+        x = (amp * 0.6 * np.cos(2 * np.pi * abs(Fc if Fc else 1e3) * 1.01 * t) + amp * 0.3 * np.cos(2 * np.pi * 0.37 * Fs / 2 * t + 1))
+        x = np.clip(x + np.random.Generator(np.random.MT19937(0x5D12000D)).integers(-amp // 8, amp // 8 + 1, size=N), -128, 127).astype(np.int8)
+        inp = os.path.join(td, name + ".in"); x.tofile(inp)
+        pre = os.path.join(td, name)
+        run(["rbb8", inp, bs, repr(Fs), repr(Fc), repr(Ff), repr(width), order, ss, pre])
+        raw = np.fromfile(pre + ".params", dtype=np.uint8)
+        hdr = raw[:32].view(np.int64); L = int(hdr[0])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), Fs=Fs, Fc=Fc, Ff=Ff, width=width, order=order, sub_sample=ss,
+                            buffer_size=bs, x=x, ref_lut_inc=int(hdr[2]), ref_neg=int(hdr[3]),
+                            ref_kernel=raw[32:32 + 8 * L].view(np.int32).reshape(L, 2),
+                            bb=np.fromfile(pre + ".bb", dtype=np.int8).reshape(-1, 2),
+                            counts=np.fromfile(pre + ".counts", dtype=np.uint32))
+        print("wrote", name, "inc=%d outputs=%d" % (hdr[2], np.fromfile(pre + ".counts", dtype=np.uint32).sum()))
+
+
 def main():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-    if "--cast-only" in sys.argv:
+    if "--cast-only" in sys.argv or "--rbb8-only" in sys.argv:
         with tempfile.TemporaryDirectory() as td:
-            gen_cast_table(td)
+            gen_cast_table(td) if "--cast-only" in sys.argv else gen_rbb8(td)
         return
     with tempfile.TemporaryDirectory() as td:
         gen_cast_table(td)
+        gen_rbb8(td)
         for (name, sc, Fs, Fc, Ff, width, order, ss, oFs, setcf, bs, N, amp, noise) in BB_CASES:
             dt = np.int16 if sc == "s16" else np.int8
             x = synth.iq_int(N, Fs, T3(amp), noise, 0x5D120000 + len(name), dt)

@@ -152,3 +152,35 @@ def test_autocast_whole_table():
     big = np.random.default_rng(3).integers(0, 256, size=1 << 20).astype(np.uint8)
     for i, o in ((3, 10), (1, 8), (9, 8), (4, 2)):
         np.testing.assert_array_equal(autocast(big, i, o), orc.autocast(big, i, o))
+
+
+@pytest.mark.parametrize("name", golden_names("rbb8_"))
+def test_real_baseband_int8_golden(name):
+    """BaseBand<int8_t> on the device == the reference's own outputs, per buffer; design (kernel, increment) identical."""
+    g = load_golden(name)
+    bs = int(g["buffer_size"])
+    bb = BaseBand(float(g["Fc"]), float(g["Ff"]), float(g["width"]), int(g["order"]), int(g["sub_sample"]), scalar="s8")
+    cfg = bb.config(sample_rate=float(g["Fs"]), buffer_size=bs)
+    assert cfg.type == _lib.T_CS8
+    k, _ = bb.design()
+    np.testing.assert_array_equal(k, g["ref_kernel"])
+    assert bb.info().lut_inc == int(g["ref_lut_inc"])
+    x = g["x"]
+    outs = [bb.process(x[o:o + bs]) for o in range(0, x.shape[0], bs)]
+    np.testing.assert_array_equal(np.array([y.shape[0] for y in outs], dtype=np.uint32), g["counts"])
+    np.testing.assert_array_equal(np.concatenate(outs), g["bb"])
+
+
+def test_real_baseband_int8_random_and_errors():
+    g = np.random.default_rng(81)
+    for trial in range(10):
+        Fs = float(g.choice([48e3, 1e6, 2.4e6])); order = int(g.integers(1, 41)); ss = int(g.choice([1, 2, 7, 16, 50, 100, 181, 200, 255, 300]))
+        Fc = float(g.choice([0.0, 1.0, -1.0]) * g.uniform(0, 0.45) * Fs); Ff = float(g.uniform(-0.4, 0.4) * Fs); width = float(g.uniform(0.001, 0.4) * Fs)
+        x = g.integers(-127, 128, size=30000).astype(np.int8)
+        bb = BaseBand(Fc, Ff, width, order, ss, scalar="s8"); bb.config(sample_rate=Fs, buffer_size=4096)
+        o = orc.BaseBand(Fc, Ff, width, order, ss, scalar=orc.S8); o.config(Fs, 4096)
+        cuts = [0, 1, 4097, 20000, 30000]
+        for s, e in zip(cuts[:-1], cuts[1:]):
+            np.testing.assert_array_equal(bb.process(x[s:e]), o.process(x[s:e]), err_msg="trial %d" % trial)
+    with pytest.raises(ConfigError):                    # int16(256 * 256) == 0: the reference would divide by zero
+        BaseBand(1e3, 1e3, 500.0, 9, 256, scalar="s8").config(sample_rate=48e3, buffer_size=1024)

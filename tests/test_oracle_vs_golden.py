@@ -155,3 +155,18 @@ def test_autocast_table_oracle_reproduces_reference():
     assert n == 24 and len(g["refused"]) == 24
     for i, o in g["refused"]:
         assert not orc.autocast_supported(int(i), int(o))
+
+
+@pytest.mark.parametrize("name", golden_names("rbb8_"))
+def test_real_baseband_int8_oracle_reproduces_reference(name):
+    """BaseBand<int8_t> (16-bit arithmetic throughout, asymmetric complex<int16_t> division): oracle == reference."""
+    g = load_golden(name)
+    o = orc.BaseBand(float(g["Fc"]), float(g["Ff"]), float(g["width"]), int(g["order"]), int(g["sub_sample"]), scalar=orc.S8)
+    bs = int(g["buffer_size"])
+    o.config(float(g["Fs"]), bs)
+    np.testing.assert_array_equal(o.kernel_i32(), g["ref_kernel"])
+    assert o.lut_inc == int(g["ref_lut_inc"])
+    x = g["x"]
+    outs = [o.process(x[k:k + bs]) for k in range(0, x.shape[0], bs)]
+    np.testing.assert_array_equal(np.array([y.shape[0] for y in outs], dtype=np.uint32), g["counts"])
+    np.testing.assert_array_equal(np.concatenate(outs), g["bb"])

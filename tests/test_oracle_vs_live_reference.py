@@ -74,6 +74,25 @@ def test_real_baseband_vs_live_reference(seed, tmp_path):
     np.testing.assert_array_equal(np.concatenate(outs), np.fromfile(pre + ".bb", dtype=np.int16).reshape(-1, 2))
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_real_baseband_int8_vs_live_reference(seed, tmp_path):
+    """BaseBand<int8_t>: 16-bit wraps in the FIR sum, the window sum and complex<int16_t>::operator/= ."""
+    g = np.random.default_rng(36000 + seed)
+    Fs, Fc, Ff, width, order, ss = _params(g)
+    if (ss * ss) % 65536 == 0:
+        ss += 1                                   # the reference divides by zero there
+    n, bs = 9000, 2048
+    amp = 127 if seed % 3 == 0 else 40
+    x = g.integers(-amp, amp + 1, size=n).astype(np.int8)
+    inp = tmp_path / "x.bin"; x.tofile(inp)
+    pre = str(tmp_path / "out")
+    subprocess.run([HARNESS, "rbb8", str(inp), str(bs), repr(Fs), repr(Fc), repr(Ff), repr(width), str(order), str(ss), pre], check=True)
+    o = orc.BaseBand(Fc, Ff, width, order, ss, scalar=orc.S8); o.config(Fs, bs)
+    outs = [o.process(x[k:k + bs]) for k in range(0, n, bs)]
+    np.testing.assert_array_equal(np.array([y.shape[0] for y in outs], dtype=np.uint32), np.fromfile(pre + ".counts", dtype=np.uint32))
+    np.testing.assert_array_equal(np.concatenate(outs), np.fromfile(pre + ".bb", dtype=np.int8).reshape(-1, 2))
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_ola_filter_vs_live_reference(seed, tmp_path):
     """FilterSink + FilterSource of the reference (with the double-precision FFT stand-in) on random bands."""
