@@ -1,8 +1,9 @@
 /* sdr_oracle.h -- CPU restatement of libsdr's receive-chain hot path.
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing under libsdr_b200/ or include/ may include, link, load or
- * execute this file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
- * --impl reference legs use it, and only as the checker or the reported CPU baseline.
+ * execute this file.  Only tests/, __graft_entry__.smoke() and bench.py (its cpu_baseline /
+ * --impl reference legs, and the c5_check that compares the gathered multi-GPU bank output with
+ * it OUTSIDE the timed region) use it, and only as the checker or the reported CPU baseline.
  *
  * Parity status: PINNED for the integer paths (IQBaseBand<int16_t>/<int8_t>, FMDemod, AMDemod,
  * USBDemod) against outputs of the reference itself, compiled from /root/reference/src by
