@@ -39,3 +39,23 @@ def test_gather_layout_gloo(world, channels):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(t == float(world) for _, _, t in res)
+
+
+def test_bank_window_layout_and_channel_ranges():
+    """Host logic of the peer-window gather: the (slot, kind) arrays tile the window without overlap, rows of every
+    rank land at disjoint offsets, and the ranges cover all channels exactly once."""
+    from libsdr_b200 import parallel
+    C_, stride = 2048, 1009
+    table, total = parallel.bank_window_layout(C_, stride)
+    spans = sorted((off, off + C_ * stride * 2) for off in table.values())
+    assert all(a1 <= b0 for (_, a1), (b0, _) in zip(spans[:-1], spans[1:])) and spans[-1][1] <= total
+    assert all(off % 256 == 0 for off in table.values())
+    for world in (1, 2, 3, 4, 8):
+        rows = []
+        for r in range(world):
+            lo, hi = parallel.channel_range(r, world, C_)
+            rows.append((lo * stride * 2, hi * stride * 2))
+            assert hi - lo in (C_ // world, C_ // world + 1)
+        assert rows[0][0] == 0 and rows[-1][1] == C_ * stride * 2
+        assert all(a1 == b0 for (_, a1), (b0, _) in zip(rows[:-1], rows[1:]))
+    assert parallel.PeerWindow.HEADER >= parallel.PeerWindow.ACK_OFFSET + 8 and parallel.PeerWindow.ACK_OFFSET >= 8 * 64
