@@ -132,6 +132,12 @@ int sdrg_iqbb_set_input_type(sdrg_iqbb *h, int type);
  * Must be called before config(). */
 int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode);
 
+/* Diagnostics (no reference counterpart): which accumulate kernel the node's last process() call launched.
+ * 0 = none yet / integer node, 1 = direct FIR, 2 = folded (batched, any window length), 3 = folded, window-pipelined
+ * (sub_sample <= 512), 4 = folded, staged short windows, 5 = folded, one thread group per window
+ * (iqbb_fold_perwin.cu), 6 = folded, TMA staging (SDRG_EXPERIMENTS builds). */
+int sdrg_iqbb_last_float_kernel(const sdrg_iqbb *h, int *which);
+
 /* What config() derived; kernel/lut are written only when non-NULL (order / 128 int32 pairs, resp.
  * float pairs for SDRG_T_F32). */
 typedef struct {

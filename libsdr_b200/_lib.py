@@ -83,6 +83,7 @@ SIGNATURES = {
     "sdrg_iqbb_set_output_sample_rate": [_V, _D],
     "sdrg_iqbb_configure": [_V, _PCFG, _PCFG],
     "sdrg_iqbb_set_float_path": [_V, _I],
+    "sdrg_iqbb_last_float_kernel": [_V, C.POINTER(C.c_int)],
     "sdrg_iqbb_set_input_type": [_V, _I],
     "sdrg_autocast_out_bytes": [_I, _I, _SZ, _PSZ],
     "sdrg_autocast_process": [_I, _I, _V, _SZ, _V],

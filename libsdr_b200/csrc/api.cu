@@ -113,6 +113,9 @@ struct sdrg_iqbb {
   int float_path = 0;                  // 0 auto, 1 direct, 2 folded
   bool fold = false;
   void *d_tab_a = nullptr, *d_tab_u = nullptr;
+  void *d_tab_v = nullptr, *d_tab_cls = nullptr;   // per-window kernel (iqbb_fold_perwin.cu): V(class, j) and phase byte -> class
+  uint32_t v_rows = 0, v_pitch = 0;
+  int last_float_kernel = 0;           // sdrg_iqbb_last_float_kernel
   uint32_t *d_work = nullptr;          // work counter of the window-pipelined kernel (0 between calls)
   // stream position
   uint32_t phase0 = 0;
@@ -189,7 +192,8 @@ Advance advance(const sdrg_iqbb *h, uint64_t n) {
 // Folded float path: A(a) and U(r,e) in double on the host (see iqbb_fold_kernels.cu).
 int upload_fold_tables(sdrg_iqbb *h) {
   const IqbbDesign &d = h->d;
-  free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
+  free_dev(&h->d_tab_a); free_dev(&h->d_tab_u); free_dev(&h->d_tab_v); free_dev(&h->d_tab_cls);
+  h->v_rows = h->v_pitch = 0;
   if (!h->d_work) SDRG_CUDA(cudaMalloc((void **)&h->d_work, sizeof(uint32_t)));
   SDRG_CUDA(cudaMemset(h->d_work, 0, sizeof(uint32_t)));
   const size_t L = d.order, ss = d.sub_sample;
@@ -227,6 +231,49 @@ int upload_fold_tables(sdrg_iqbb *h) {
   SDRG_CUDA(cudaMemcpy(h->d_tab_a, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice));
   SDRG_CUDA(cudaMalloc(&h->d_tab_u, U.size() * sizeof(float)));
   SDRG_CUDA(cudaMemcpy(h->d_tab_u, U.data(), U.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // Window-direct kernel (short windows): V(r, j) = sum_{d = max(0, j-L+1)}^{min(j, ss-1)} B(r, d) k[j-d], j < ss+L-1.
+  // B(r, d) depends on r only through the carry [r + (d inc & 255) >= 256], which is monotone in r: equal carry
+  // patterns give equal rows, so rows are stored once per pattern (<= ss + 1 of them) and cls[r] names the row.
+  if (ss <= 256) {
+    const size_t len = ss + L - 1, pitch = len | 1;
+    std::vector<uint16_t> cls(256);
+    std::vector<float> V;
+    std::vector<uint64_t> sig(ss), prev(ss);
+    std::vector<double> dr(ss), di(ss);
+    size_t rows = 0;
+    for (size_t r = 0; r < 256; ++r) {
+      for (size_t dd = 0; dd < ss; ++dd) sig[dd] = nco ? ((r + dd * inc) >> 8) : 0;
+      if (r == 0 || sig != prev) {
+        if ((rows + 1) * pitch * 8 > 160 * 1024) { rows = 0; break; }      // would not fit next to a tile: no direct kernel
+        for (size_t dd = 0; dd < ss; ++dd) {
+          if (!nco) { dr[dd] = 1.0; di[dd] = 0.0; continue; }
+          const size_t idx = neg ? (size_t)((127 + 128 - (sig[dd] % 128)) % 128) : (size_t)(sig[dd] % 128);
+          dr[dd] = d.lutd_re[idx]; di[dd] = d.lutd_im[idx];
+        }
+        V.resize(2 * (rows + 1) * pitch, 0.0f);
+        for (size_t j = 0; j < len; ++j) {
+          double sr = 0, si = 0;
+          const size_t d_lo = j + 1 > L ? j + 1 - L : 0, d_hi = j < ss - 1 ? j : ss - 1;
+          for (size_t dd = d_lo; dd <= d_hi; ++dd) {
+            const double kr = d.kd_re[j - dd], ki = d.kd_im[j - dd];
+            sr += dr[dd] * kr - di[dd] * ki;
+            si += dr[dd] * ki + di[dd] * kr;
+          }
+          V[2 * (rows * pitch + j)] = (float)sr; V[2 * (rows * pitch + j) + 1] = (float)si;
+        }
+        ++rows;
+        prev = sig;
+      }
+      cls[r] = (uint16_t)(rows - 1);
+    }
+    if (rows) {
+      SDRG_CUDA(cudaMalloc(&h->d_tab_v, V.size() * sizeof(float)));
+      SDRG_CUDA(cudaMemcpy(h->d_tab_v, V.data(), V.size() * sizeof(float), cudaMemcpyHostToDevice));
+      SDRG_CUDA(cudaMalloc(&h->d_tab_cls, cls.size() * sizeof(uint16_t)));
+      SDRG_CUDA(cudaMemcpy(h->d_tab_cls, cls.data(), cls.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      h->v_rows = (uint32_t)rows; h->v_pitch = (uint32_t)pitch;
+    }
+  }
   return SDRG_OK;
 }
 
@@ -371,14 +418,17 @@ int run_call(sdrg_iqbb *h, const void *d_in, uint32_t n, void *d_bb, void *d_aud
     IqbbFoldArgs fa{};
     fa.x = d_in; fa.acc_cur = a.acc_cur; fa.acc_next = a.acc_next;
     fa.tab_a = (const float2 *)h->d_tab_a; fa.tab_u = (const float2 *)h->d_tab_u;
+    fa.tab_v = (const float2 *)h->d_tab_v; fa.tab_cls = (const uint16_t *)h->d_tab_cls;
+    fa.v_rows = h->v_rows; fa.v_pitch = h->v_pitch;
     fa.n = n; fa.taps_len = (uint32_t)h->d.order; fa.ss = a.ss; fa.r0 = a.r0; fa.first = a.first;
     fa.phase0 = a.nco ? a.phase0 : 0u; fa.inc = a.nco ? a.inc : 0u;
     fa.zero_next = a.zero_next; fa.variant = h->float_path == 3 ? 2u : 0u;
     fa.work = h->d_work; f.work_reset = h->d_work;
     ProfScope ps(SDRG_KERNEL_IQBB_ACCUM, st);
-    rc = launch_iqbb_fold(fa, st);
+    rc = launch_iqbb_fold(fa, st, &h->last_float_kernel);
   } else {
     ProfScope ps(SDRG_KERNEL_IQBB_ACCUM, st);
+    if (h->d.scalar == SDRG_T_F32) h->last_float_kernel = 1;
     rc = launch_iqbb_accum(h->d.scalar, a, st);
   }
   if (rc) return rc;
@@ -714,7 +764,7 @@ int sdrg_iqbb_destroy(sdrg_iqbb *h) {
   free_dev(&h->d_taps); free_dev(&h->d_lut);
   free_dev(&h->d_hist[0]); free_dev(&h->d_hist[1]);
   free_dev(&h->d_acc[0]); free_dev(&h->d_acc[1]);
-  free_dev(&h->d_tab_a); free_dev(&h->d_tab_u);
+  free_dev(&h->d_tab_a); free_dev(&h->d_tab_u); free_dev(&h->d_tab_v); free_dev(&h->d_tab_cls);
   if (h->d_work) { cudaFree(h->d_work); h->d_work = nullptr; }
   free_dev(&h->d_in); free_dev(&h->d_out);
   delete h;
@@ -819,6 +869,12 @@ int sdrg_iqbb_set_float_path(sdrg_iqbb *h, int mode) {
 #endif
   if (h->configured) return set_error(SDRG_ERR_RUNTIME, "IQBaseBand: select the float path before config()");
   h->float_path = mode;
+  return SDRG_OK;
+}
+
+int sdrg_iqbb_last_float_kernel(const sdrg_iqbb *h, int *which) {
+  if (!h || !which) return set_error(SDRG_ERR_ARG, "null argument");
+  *which = h->last_float_kernel;
   return SDRG_OK;
 }
 

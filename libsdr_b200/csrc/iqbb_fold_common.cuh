@@ -85,11 +85,15 @@ __device__ __forceinline__ bool chunk_of(const IqbbFoldArgs &a, uint32_t id, int
 }
 
 // One chunk on the general path: any clipping, any piece of a long window, any tap count.
+// `what`: bit 0 = add the samples' contributions to their own window, bit 1 = add the tails they owe to the next one
+// (the per-window kernel computes whole windows itself and needs only one of the two from its neighbours);
+// STAGED = false reduces with shuffles and issues the RED.ADDs at once (no per-warp staging rows needed).
+template <bool STAGED = true>
 __device__ __forceinline__ void fold_chunk_general(const IqbbFoldArgs &a, const uint32_t id, const uint32_t total_warps,
                                                    const float2 *__restrict__ x, const float2 *sA, const float2 *sH,
                                                    const int lane, const int L1, const int win_off,
                                                    const uint32_t inc32, const uint32_t inc256,
-                                                   WarpStage &stage, float *acc_out) {
+                                                   WarpStage &stage, float *acc_out, const uint32_t what = 3u) {
     Chunk c;
     if (lane == 0 && a.pf_dist && id + a.pf_dist * total_warps < a.n_chunks) {   // a later chunk of this warp -> L2, one instruction
       Chunk nx;
@@ -151,12 +155,21 @@ __device__ __forceinline__ void fold_chunk_general(const IqbbFoldArgs &a, const 
     float2 tot = make_float2(-sent.x, -sent.y);
 #pragma unroll
     for (int u = 0; u < 8; ++u) cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);   // H_u = U(r_u, 0)
-    stage.push(tot, c.s, lane, acc_out);
-    if (c.t_lo < len) stage.push(sent, c.s + 1, lane, acc_out);
+    if (STAGED) {
+      if (what & 1u) stage.push(tot, c.s, lane, acc_out);
+      if (c.t_lo < len && (what & 2u)) stage.push(sent, c.s + 1, lane, acc_out);
+    } else {
+      if (what & 1u) flush(acc_out, c.s, tot, lane);
+      if (c.t_lo < len && (what & 2u)) flush(acc_out, c.s + 1, sent, lane);
+    }
 }
 
 
 }  // namespace foldk
+
+// iqbb_fold_perwin.cu: whole windows per thread group (short windows); false when the call has no eligible window
+bool fold_perwin_eligible(IqbbFoldArgs &a);
+int launch_fold_perwin(const IqbbFoldArgs &a, cudaStream_t st);
 
 // iqbb_fold_experimental.cu
 int launch_fold_tma(IqbbFoldArgs a, cudaStream_t st);                 // opt-in TMA bulk-copy staging (float path 3)

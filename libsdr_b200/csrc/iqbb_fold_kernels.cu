@@ -403,7 +403,7 @@ static int launch_fold_small(const IqbbFoldArgs &a, cudaStream_t st) {
 }  // namespace
 
 // Grids are sized to the machine: 148 SMs x 3 resident CTAs of 8 warps.
-static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
+static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st, int *which) {
   // slots touched by this call: slot of the last sample + 1
   const uint64_t q_last = (uint64_t)a.r0 + (a.n - 1) - ((a.first && a.n > 1) ? 1 : 0);
   const uint64_t n_slots = q_last / a.ss + 1;
@@ -433,9 +433,11 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
 #else
   constexpr int probe = 0;
 #endif
+  static const int perwin_max = env_int("SDRG_FOLD_PERWIN_MAX", 64);   // longest window taken by the per-window kernel (iqbb_fold_perwin.cu)
+  if (!probe && a.cpw == 1 && (int)a.ss <= perwin_max && fold_perwin_eligible(a)) { *which = 5; return launch_fold_perwin(a, st); }
   static const int small_env = env_int("SDRG_FOLD_SMALL", 55);   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
-  if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) return launch_fold_small(a, st);
-  if (!probe && win_env && a.fast && a.ss <= 512 && a.fast_hi >= 1) return launch_fold_win(a, st);
+  if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) { *which = 4; return launch_fold_small(a, st); }
+  if (!probe && win_env && a.fast && a.ss <= 512 && a.fast_hi >= 1) { *which = 3; return launch_fold_win(a, st); }
 #ifdef SDRG_EXPERIMENTS
   if (probe >= 1 && probe <= 3) return launch_fold_probe(probe, a, st);
 #endif
@@ -449,6 +451,7 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
     SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_f32_kernel, kFoldThreads, smem));
     resident_dev[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
+  *which = 2;
   const int resident = resident_dev[dev];
   const uint64_t want = (n_chunks + kFoldWarps - 1) / kFoldWarps;
   const unsigned grid = (unsigned)(want < (uint64_t)resident ? want : (uint64_t)resident);
@@ -457,18 +460,20 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st) {
   return SDRG_OK;
 }
 
-int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st) {
+int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st, int *which_out) {
+  int which_local = 0;
+  int *which = which_out ? which_out : &which_local;
   if (a.n == 0) return SDRG_OK;
   // bulk async copies need 16-byte aligned global addresses; otherwise use the LDG variant
   const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0;
 #ifdef SDRG_EXPERIMENTS
   static const int env_variant = env_int("SDRG_FOLD_VARIANT", 0);
   const int variant = a.variant ? (int)a.variant : env_variant;      // 2 = TMA staging (iqbb_fold_experimental.cu)
-  if (aligned && variant == 2 && a.ss >= 32) return launch_fold_tma(a, st);
+  if (aligned && variant == 2 && a.ss >= 32) { *which = 6; return launch_fold_tma(a, st); }
 #else
   (void)aligned;
 #endif
-  return launch_fold_ldg(a, st);
+  return launch_fold_ldg(a, st, which);
 }
 
 }  // namespace sdrg

@@ -68,6 +68,11 @@ struct IqbbFoldArgs {
   uint32_t      fast_hi;    // chunk ids 1..fast_hi are complete interior windows (0 = none)
   uint32_t     *work;       // window-pipelined kernel: work counter (0 at launch; the finalize kernel resets it)
   uint32_t      work_chunk; // consecutive windows per grab
+  // per-window kernel (short windows), see iqbb_fold_perwin.cu: V(class, j), one row per distinct carry pattern
+  const float2 *tab_v;      // v_rows x v_pitch, or null when the table is not built (window too long / table too large)
+  const uint16_t *tab_cls;  // 256 entries: low phase byte at a window's first sample -> row of tab_v
+  uint32_t      v_rows, v_pitch;
+  uint32_t      d_lo, d_hi; // slots d_lo..d_hi are complete windows whose L-1 halo samples lie inside this call (filled in by the launcher)
 };
 
 // finalize (+ optional demodulation) of the completed windows of one call
@@ -108,7 +113,7 @@ int launch_iqbb_accum(int scalar, const IqbbAccumArgs &a, cudaStream_t st);
 int launch_bank_accum(int scalar, const BankAccumArgs &a, cudaStream_t st);
 int launch_bank_finalize(int scalar, const IqbbFinalizeArgs &a, const BankFinalizeStrides &s, uint32_t channels, cudaStream_t st);
 int launch_iqbb_finalize(int scalar, const IqbbFinalizeArgs &a, cudaStream_t st);
-int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st);
+int launch_iqbb_fold(const IqbbFoldArgs &a, cudaStream_t st, int *which = nullptr);   // *which: see sdrg_iqbb_last_float_kernel
 
 // stand-alone demodulators (demod_kernels.cu)
 int launch_fmdemod(int scalar, const void *in, size_t n, void *out, const void *last_in, void *last_out,

@@ -104,6 +104,12 @@ class IQBaseBand:
         """f32 only: 0 auto, 1 direct kernel, 2 folded kernel (before config())."""
         _lib.call("sdrg_iqbb_set_float_path", self._h, int(mode))
 
+    def lastFloatKernel(self):
+        """Diagnostics: 1 direct FIR, 2 folded batched, 3 window-pipelined, 4 staged short windows, 5 per-window, 6 TMA."""
+        w = C.c_int(0)
+        _lib.call("sdrg_iqbb_last_float_kernel", self._h, C.byref(w))
+        return w.value
+
     def config(self, src_cfg=None, *, type=None, sample_rate=0.0, buffer_size=0, num_buffers=1):
         """config(const Config&) (baseband.hh:115-132). Raises ConfigError on a type mismatch."""
         if src_cfg is None:

@@ -22,4 +22,12 @@ for ss, order in cases:
     for _ in range(7):
         e0.record(); bb.process(x); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ts.sort(); ms = ts[len(ts) // 2]
+    _lib.profile_enable(True)
+    for _ in range(5):
+        bb.process(x)
+    torch.cuda.synchronize()
+    kms, kn = _lib.profile_read(_lib.KERNEL_IQBB_ACCUM)
+    fms, fn = _lib.profile_read(_lib.KERNEL_IQBB_FINALIZE)
+    _lib.profile_enable(False)
+    print("   kernel %d: accumulate %.3f ms = %.1f GB/s, finalize %.3f ms" % (bb.lastFloatKernel(), kms / max(kn, 1), n * 8 / (kms / max(kn, 1)) / 1e6, fms / max(fn, 1)))
     print("ss=%6d L=%3d  %7.3f ms  %7.1f GB/s (whole call incl. finalize)" % (ss, order, ms, n * 8 / ms / 1e6), flush=True)
