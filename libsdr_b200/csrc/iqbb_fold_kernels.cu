@@ -433,7 +433,7 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st, int *which) {
 #else
   constexpr int probe = 0;
 #endif
-  static const int perwin_max = env_int("SDRG_FOLD_PERWIN_MAX", 64);   // longest window taken by the per-window kernel (iqbb_fold_perwin.cu)
+  static const int perwin_max = env_int("SDRG_FOLD_PERWIN_MAX", 256);   // longest window taken by the per-window kernel (iqbb_fold_perwin.cu)
   if (!probe && a.cpw == 1 && (int)a.ss <= perwin_max && fold_perwin_eligible(a)) { *which = 5; return launch_fold_perwin(a, st); }
   static const int small_env = env_int("SDRG_FOLD_SMALL", 55);   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
   if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) { *which = 4; return launch_fold_small(a, st); }

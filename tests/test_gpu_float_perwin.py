@@ -32,7 +32,7 @@ def _table_fits(order, ss):
 
 @pytest.mark.parametrize("ss,order", [(2, 2), (2, 3), (3, 4), (7, 8), (8, 9), (15, 15), (16, 15), (16, 17), (17, 5), (24, 25),
                                       (31, 15), (32, 15), (33, 34), (48, 20), (50, 15), (63, 33), (64, 32), (64, 65), (65, 64),
-                                      (80, 32), (96, 64), (100, 15), (127, 100), (128, 20), (128, 64)])
+                                      (80, 32), (96, 64), (100, 15), (127, 100), (128, 20), (128, 64), (200, 30), (256, 16), (256, 257)])
 @pytest.mark.parametrize("Fc", [1.25e6, -1.25e6, 0.0, 333e3], ids=["pos", "neg", "zero", "frac"])
 def test_per_window_kernel_geometries(ss, order, Fc):
     n = 300000
