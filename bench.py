@@ -501,7 +501,8 @@ def secondary_workloads(coll, dev, x_c2):
     try:   # the float path off the C2 geometry: short windows, long windows, many taps
         xf = x_c2                                                           # the headline batch: 256 Mi samples = 2 GiB
         n = xf.shape[0]
-        shapes = [("ss16_15taps", 15, 16), ("ss50_15taps", 15, 50), ("ss64_32taps", 32, 64), ("ss416_64taps_c2", 64, 416),
+        shapes = [("ss16_15taps", 15, 16), ("ss24_25taps", 25, 24), ("ss50_15taps", 15, 50), ("ss64_32taps", 32, 64), ("ss128_20taps", 20, 128),
+                  ("ss416_64taps_c2", 64, 416),
                   ("ss1000_64taps", 64, 1000), ("ss4096_64taps", 64, 4096), ("ss20000_64taps", 64, 20000), ("ss416_128taps", 128, 416)]
         fl = {}
         for name, order, ss in shapes:
@@ -510,7 +511,10 @@ def secondary_workloads(coll, dev, x_c2):
             ch = RxChain(bb, DEMOD_FM)
             ms = timed(lambda: ch.process(xf, 1 << 20))
             gbs = (8 + 4 / ss) * n / ms / 1e6
-            fl[name] = {"order": order, "sub_sample": ss, "msamples_per_s": n / ms / 1e3, "algorithmic_gbs": gbs, "hbm_frac": gbs / peak}
+            kern = {1: "direct FIR", 2: "folded, batched", 3: "folded, window-pipelined", 4: "folded, staged short windows",
+                    5: "folded, per-window (V table)", 6: "folded, TMA staging"}.get(bb.lastFloatKernel(), "?")
+            fl[name] = {"order": order, "sub_sample": ss, "msamples_per_s": n / ms / 1e3, "algorithmic_gbs": gbs, "hbm_frac": gbs / peak,
+                        "kernel": kern}
             del ch, bb
         out["float_shapes"] = fl
     except Exception as e:  # pragma: no cover

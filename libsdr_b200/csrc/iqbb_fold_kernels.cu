@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kFoldThreads, 4) iqbb_fold_f32_kernel(const Iq
 // constant (S x 256 B) and a window costs no exposed memory round trip -- the two per window of the
 // batched schedule above were what kept it at ~92 % of HBM.  Edge chunks (window 0, the clipped
 // last window) go through fold_chunk_general.
-template <int S, int P = 0>     // P != 0: timing experiments only (bit 0 no tails, bit 1 no A lookup, bit 2 no H weighting)
+template <int S, int P = 0, int TS = 3>     // TS: ring steps that can hold tail samples (3: taps <= 65, 5: taps <= 129); P != 0: timing experiments only (bit 0 no tails, bit 1 no A lookup, bit 2 no H weighting)
 __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) iqbb_fold_f32_win_kernel(const IqbbFoldArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ float2 sA[128];
@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
   const int win_off = (int)a.first - (int)a.r0;
   const uint32_t inc32 = (32u * a.inc) & 0x7fffu, inc256 = (256u * a.inc) & 0x7fffu;
   const bool last_ok = (uint32_t)lane < a.fast_pl;
-  int te[3]; bool te_ok[3];                   // tail distance of this lane's sample in ring step S-1-k
+  int te[TS]; bool te_ok[TS];                 // tail distance of this lane's sample in ring step S-1-k
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { te[k] = (int)a.ss - 32 * (S - 1 - k) - lane; te_ok[k] = te[k] >= 1 && te[k] <= L1; }
+  for (int k = 0; k < TS; ++k) { te[k] = (int)a.ss - 32 * (S - 1 - k) - lane; te_ok[k] = te[k] >= 1 && te[k] <= L1; }
 
   // Edge chunks (window 0, the clipped last window and the tails behind it) are dealt statically ...
   if (wg == 0) fold_chunk_general(a, 0u, T, x, sA, sH, lane, L1, win_off, inc32, inc256, stage, acc_out);
@@ -191,14 +191,14 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
       const float2 *__restrict__ xn = x + ((int)(nid * a.ss) + win_off) + lane;
       const uint32_t ph = a.phase0 + (uint32_t)(c_lo + lane) * a.inc;      // only bits 0..14 are used
       const uint32_t pb = a.phase0 + (uint32_t)(c_lo + (int)a.ss) * a.inc;
-      // Tails owed to the next window: the last L-1 samples of the window sit in the last (up to three)
+      // Tails owed to the next window: the last L-1 samples of the window sit in the last (up to TS)
       // ring steps already, so only their weights U(r_b, e), e = ss - 32 i - lane, are fetched (issued
       // now, used ~a window later).  e and its validity are per-lane constants of the launch.
       const float2 Ab = sA[(pb & 0x7fffu) >> 8];
       const float2 *__restrict__ urow = a.tab_u + (size_t)(pb & 255u) * a.taps_len;
-      float2 ut[3];
+      float2 ut[TS];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < TS; ++k) {
         ut[k] = make_float2(0.f, 0.f);
         if (!(P & 1) && k < S && te_ok[k]) ut[k] = (P & 8) ? Ab : __ldg(urow + te[k]);
       }
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
       for (int i = 0; i < S; ++i) {
         if (P & 2) cfma(R[i & 7], Ab, ring[i]);
         else cfma(R[i & 7], sA[((ph + i * inc32) & 0x7fffu) >> 8], ring[i]);
-        if (!(P & 1) && S - 1 - i < 3) cfma(ts, ut[S - 1 - i], ring[i]);     // zero weight outside the tail
+        if (!(P & 1) && S - 1 - i < TS) cfma(ts, ut[S - 1 - i], ring[i]);    // zero weight outside the tail
         if (more) {
           if (i + 1 < S) ring[i] = ld_stream(xn + 32 * i);
           else if (last_ok) ring[i] = ld_stream(xn + 32 * i);    // lanes past the window keep their zero
@@ -237,21 +237,21 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
   stage.drain(lane, acc_out);
 }
 
-template <int S, int P = 0>
+template <int S, int P = 0, int TS = 3>
 static int launch_fold_win_s(const IqbbFoldArgs &a, cudaStream_t st) {
   static std::atomic<int> resident_dev[kMaxDevices];
   const size_t smem = (size_t)kFoldWarps * kStageRows * kStagePitch * sizeof(float2);
   const int dev = current_device();
   if (!resident_dev[dev]) {
-    SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_win_kernel<S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDRG_CUDA(cudaFuncSetAttribute(iqbb_fold_f32_win_kernel<S, P, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 0, per_sm = 0;
     SDRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_f32_win_kernel<S, P>, kFoldThreads, smem));
+    SDRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, iqbb_fold_f32_win_kernel<S, P, TS>, kFoldThreads, smem));
     resident_dev[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
   const uint64_t resident = (uint64_t)resident_dev[dev];
   const uint64_t want = ((uint64_t)a.n_chunks + kFoldWarps - 1) / kFoldWarps;
-  iqbb_fold_f32_win_kernel<S, P><<<(unsigned)(want < resident ? want : resident), kFoldThreads, smem, st>>>(a);
+  iqbb_fold_f32_win_kernel<S, P, TS><<<(unsigned)(want < resident ? want : resident), kFoldThreads, smem, st>>>(a);
   SDRG_CHECK_LAUNCH("iqbb_fold_f32_win_kernel");
   return SDRG_OK;
 }
@@ -268,6 +268,18 @@ static int launch_fold_win(const IqbbFoldArgs &a, cudaStream_t st) {
     }
   }
 #endif
+  if (a.taps_len > 65) {      // 66..129 taps: the tail reaches back up to five ring steps (ss >= taps - 1 >= 65, so S >= 3)
+    switch ((a.ss + 31) / 32) {
+      case 3: return launch_fold_win_s<3, 0, 5>(a, st);   case 4: return launch_fold_win_s<4, 0, 5>(a, st);
+      case 5: return launch_fold_win_s<5, 0, 5>(a, st);   case 6: return launch_fold_win_s<6, 0, 5>(a, st);
+      case 7: return launch_fold_win_s<7, 0, 5>(a, st);   case 8: return launch_fold_win_s<8, 0, 5>(a, st);
+      case 9: return launch_fold_win_s<9, 0, 5>(a, st);   case 10: return launch_fold_win_s<10, 0, 5>(a, st);
+      case 11: return launch_fold_win_s<11, 0, 5>(a, st); case 12: return launch_fold_win_s<12, 0, 5>(a, st);
+      case 13: return launch_fold_win_s<13, 0, 5>(a, st); case 14: return launch_fold_win_s<14, 0, 5>(a, st);
+      case 15: return launch_fold_win_s<15, 0, 5>(a, st); case 16: return launch_fold_win_s<16, 0, 5>(a, st);
+      default: return set_error(SDRG_ERR_RUNTIME, "IQBaseBand<float>: window-pipelined kernel needs 65 <= sub_sample <= 512 for more than 65 taps");
+    }
+  }
   switch ((a.ss + 31) / 32) {
     case 1: return launch_fold_win_s<1>(a, st);   case 2: return launch_fold_win_s<2>(a, st);
     case 3: return launch_fold_win_s<3>(a, st);   case 4: return launch_fold_win_s<4>(a, st);
@@ -416,12 +428,13 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st, int *which) {
   static const int pf = env_int("SDRG_FOLD_PF", 0);   // measured: no gain with round-robin chunks
   a.pf_dist = (uint32_t)pf;
   static const int fast_env = env_int("SDRG_FOLD_FAST", 1);
-  a.fast = (fast_env && a.cpw == 1 && a.taps_len <= 65 && a.ss + 1 >= a.taps_len) ? 1u : 0u;
+  a.fast = (fast_env && a.cpw == 1 && a.taps_len <= 65 && a.ss + 1 >= a.taps_len) ? 1u : 0u;   // batched kernel: two tail steps
+  const bool win_ok = fast_env && a.cpw == 1 && a.taps_len <= 129 && a.ss + 1 >= a.taps_len && a.ss <= 512;   // window-pipelined: up to five
   a.fast_nb = a.ss / 256;
   a.fast_rs = (a.ss % 256 + 31) / 32;
   a.fast_pl = a.ss % 32 ? a.ss % 32 : 32;
   a.fast_hi = 0;
-  if (a.fast) {      // ids 1..fast_hi: (id + 1) * ss + first - r0 <= n
+  if (a.fast || win_ok) {      // ids 1..fast_hi: (id + 1) * ss + first - r0 <= n
     const int64_t hi = ((int64_t)a.n + (int64_t)a.r0 - (int64_t)a.first) / (int64_t)a.ss - 1;
     a.fast_hi = hi >= 1 ? (uint32_t)hi : 0u;
   }
@@ -437,7 +450,7 @@ static int launch_fold_ldg(IqbbFoldArgs a, cudaStream_t st, int *which) {
   if (!probe && a.cpw == 1 && (int)a.ss <= perwin_max && fold_perwin_eligible(a)) { *which = 5; return launch_fold_perwin(a, st); }
   static const int small_env = env_int("SDRG_FOLD_SMALL", 55);   // largest ss taken by the short-window kernel (measured crossover with the window-pipelined one)
   if (!probe && a.cpw == 1 && a.ss + 1 >= a.taps_len && (a.ss < 32 || (int)a.ss <= small_env)) { *which = 4; return launch_fold_small(a, st); }
-  if (!probe && win_env && a.fast && a.ss <= 512 && a.fast_hi >= 1) { *which = 3; return launch_fold_win(a, st); }
+  if (!probe && win_env && win_ok && a.fast_hi >= 1) { *which = 3; return launch_fold_win(a, st); }
 #ifdef SDRG_EXPERIMENTS
   if (probe >= 1 && probe <= 3) return launch_fold_probe(probe, a, st);
 #endif

@@ -333,6 +333,7 @@ def test_float_small_configs(demod, path):
 
 
 @pytest.mark.parametrize("ss,order", [(32, 33), (33, 2), (63, 64), (64, 64), (100, 2), (416, 1), (417, 64), (512, 65), (513, 65), (600, 40),
+                                      (127, 128), (130, 129), (200, 129), (300, 66), (416, 128), (512, 100), (512, 129), (513, 129), (416, 130),
                                       (768, 64), (1000, 64), (2083, 15), (5000, 64), (8191, 64), (8192, 64), (8193, 64), (300000, 128)])
 @pytest.mark.parametrize("path", [2, 3], ids=["folded", "folded-tma"])
 def test_float_folded_geometry(ss, order, path):
