@@ -260,9 +260,12 @@ __global__ void __launch_bounds__(1024, 1) iqbb_fold_f32_perwin16_kernel(const I
 
   uint32_t stage = 0, phases = 0;
   for (uint32_t t = vcta; t < geo.n_tiles; t += vgrid) {
-    mbar_wait(smem_u32(&bars[grp][stage]), (phases >> stage) & 1u);           // the bulk copies of tile t have landed
+    // One warp polls the tile's mbarrier (256 spinning threads would take issue slots from the groups that are summing);
+    // the group's named barrier then publishes the landed tile to the other warps and, at the same time, tells the
+    // first warp that everybody is done with tile t-1, whose buffer the next bulk copies overwrite.
+    if (gwarp == 0) mbar_wait(smem_u32(&bars[grp][stage]), (phases >> stage) & 1u);
     phases ^= 1u << stage;
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kPwGroup) : "memory");    // the group is done with tile t-1: its buffer is free
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kPwGroup) : "memory");
     issue_tile(t + (stages - 1) * vgrid, stage == 0 ? stages - 1 : stage - 1);
     const float2 *xs = sX + (size_t)stage * geo.x_tile + par;
     const uint32_t s0 = a.d_lo + t * TW;

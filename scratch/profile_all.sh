@@ -13,4 +13,6 @@ $NCU --kernel-name regex:fft8k --launch-skip 1 -o gpurun_out/r02_fft8k python sc
 $NCU --kernel-name regex:iqbb_accum_int_warp --launch-skip 2 -o gpurun_out/r02_int16_warp python scratch/c1_only.py > /dev/null 2>&1
 $NCU --kernel-name regex:iqbb_accum_int_warp --launch-skip 25 -o gpurun_out/r02_int16_warp_realsym python scratch/c1_only.py > /dev/null 2>&1
 $NCU --kernel-name regex:bank_accum --launch-skip 2 -o gpurun_out/r02_bank python scratch/bank_probe.py > /dev/null 2>&1
+$NCU --kernel-name regex:perwin16 --launch-skip 2 -o gpurun_out/r02_perwin16_ss64 python scratch/float_sweep.py 64,32 > /dev/null 2>&1
+$NCU --kernel-name regex:perwin1_ --launch-skip 2 -o gpurun_out/r02_perwin1_ss16 python scratch/float_sweep.py 16,15 > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
