@@ -191,6 +191,27 @@ __global__ void __launch_bounds__(kPw1Threads, 4) iqbb_fold_f32_perwin1_kernel(c
   cp_async_wait<0>();
 }
 
+// One window of a half warp, NS steps of 16 lanes fully unrolled (immediate offsets, no loop): the last step is the only
+// one that can be partial.  NS = 0: any number of steps (loop).
+template <int NS>
+__device__ __forceinline__ float2 mac_window(const float2 *__restrict__ pv, const float2 *__restrict__ px, int n_steps, bool last_ok) {
+  float2 b0 = make_float2(0.f, 0.f), b1 = b0;
+  if (NS > 0) {
+#pragma unroll
+    for (int s = 0; s + 1 < NS; ++s) cfma((s & 1) ? b1 : b0, pv[16 * s], px[16 * s]);
+    if (last_ok) cfma(((NS - 1) & 1) ? b1 : b0, pv[16 * (NS - 1)], px[16 * (NS - 1)]);
+  } else {
+    int s = 0;
+    for (; s + 3 <= n_steps; s += 2, pv += 32, px += 32) {
+      const float2 v0 = pv[0], v1 = pv[16], x0 = px[0], x1 = px[16];
+      cfma(b0, v0, x0); cfma(b1, v1, x1);
+    }
+    if (s + 2 <= n_steps) { cfma(b0, pv[0], px[0]); pv += 16; px += 16; }
+    if (last_ok) cfma(b1, pv[0], px[0]);
+  }
+  return make_float2(b0.x + b1.x, b0.y + b1.y);
+}
+
 // ---- ss >= 28: a half warp per window ----------------------------------------------------------------------------
 // The V table exists once per CTA and can take most of the shared memory, so there is ONE CTA per SM; to keep the SM
 // busy across tile hand-overs the CTA is split into groups of 256 threads that run independent tile pipelines (own ring
@@ -253,10 +274,13 @@ __global__ void __launch_bounds__(1024, 1) iqbb_fold_f32_perwin16_kernel(const I
   perwin_edges(a, geo, sA, sH);
 
   const int l16 = tid & 15, hw = gt >> 4;
-  const int n_full = len >> 4;                          // steps with all 16 lanes
-  const bool tail_ok = l16 < (len & 15);                // ... and this lane's part of the last, partial step
-  const int w_mine = hw * K + ((l16 * K) >> 4);         // the window whose total this lane holds after reduce16()
+  const int n_steps = (len + 15) >> 4;                              // steps of 16 lanes; only the last one can be partial
+  const bool last_ok = (len & 15) == 0 || l16 < (len & 15);         // this lane's part of it
+  const int w_mine = hw * K + ((l16 * K) >> 4);                     // the window whose total this lane holds after reduce16()
   const bool writer = (l16 & (16 / K - 1)) == 0;
+  const uint32_t ph_step = a.ss * a.inc;                            // phase advance per window
+  const uint32_t ph_mine = (uint32_t)((int)(hw * K * a.ss) + win_off) * a.inc + a.phase0;     // + s0 * ph_step: phase of this half warp's first window
+  const int x_mine = hw * K * ss + l16;
 
   uint32_t stage = 0, phases = 0;
   for (uint32_t t = vcta; t < geo.n_tiles; t += vgrid) {
@@ -267,32 +291,35 @@ __global__ void __launch_bounds__(1024, 1) iqbb_fold_f32_perwin16_kernel(const I
     phases ^= 1u << stage;
     asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kPwGroup) : "memory");
     issue_tile(t + (stages - 1) * vgrid, stage == 0 ? stages - 1 : stage - 1);
-    const float2 *xs = sX + (size_t)stage * geo.x_tile + par;
+    const float2 *xs = sX + (size_t)stage * geo.x_tile + par + x_mine;
     const uint32_t s0 = a.d_lo + t * TW;
     const int nw = (int)min((uint32_t)TW, a.d_hi + 1 - s0);
+    const uint32_t ph0 = ph_mine + s0 * ph_step;
     float2 acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       acc[k] = make_float2(0.f, 0.f);
-      const int wl = hw * K + k;
-      if (wl < nw) {
-        const uint32_t phb = a.phase0 + (uint32_t)((int)((s0 + wl) * a.ss) + win_off) * a.inc;
+      if (hw * K + k < nw) {
+        const uint32_t phb = ph0 + k * ph_step;
         const float2 *pv = sV + (uint32_t)sC[phb & 255u] * a.v_pitch + l16;
-        const float2 *px = xs + wl * ss + l16;
-        float2 b0 = make_float2(0.f, 0.f), b1 = b0;
-        int s = 0;
-        for (; s + 2 <= n_full; s += 2, pv += 32, px += 32) {
-          const float2 v0 = pv[0], v1 = pv[16], x0 = px[0], x1 = px[16];
-          cfma(b0, v0, x0); cfma(b1, v1, x1);
+        const float2 *px = xs + k * ss;
+        switch (n_steps) {        // CTA-uniform
+          case 2: acc[k] = mac_window<2>(pv, px, n_steps, last_ok); break;
+          case 3: acc[k] = mac_window<3>(pv, px, n_steps, last_ok); break;
+          case 4: acc[k] = mac_window<4>(pv, px, n_steps, last_ok); break;
+          case 5: acc[k] = mac_window<5>(pv, px, n_steps, last_ok); break;
+          case 6: acc[k] = mac_window<6>(pv, px, n_steps, last_ok); break;
+          case 7: acc[k] = mac_window<7>(pv, px, n_steps, last_ok); break;
+          case 8: acc[k] = mac_window<8>(pv, px, n_steps, last_ok); break;
+          case 9: acc[k] = mac_window<9>(pv, px, n_steps, last_ok); break;
+          case 10: acc[k] = mac_window<10>(pv, px, n_steps, last_ok); break;
+          default: acc[k] = mac_window<0>(pv, px, n_steps, last_ok); break;
         }
-        if (s < n_full) { cfma(b0, pv[0], px[0]); pv += 16; px += 16; }
-        if (tail_ok) cfma(b1, pv[0], px[0]);
-        acc[k] = make_float2(b0.x + b1.x, b0.y + b1.y);
       }
     }
     const float2 tot = reduce16<K>(acc, l16);
     if (writer && w_mine < nw) {
-      const uint32_t phb = a.phase0 + (uint32_t)((int)((s0 + w_mine) * a.ss) + win_off) * a.inc;
+      const uint32_t phb = ph0 + (uint32_t)((l16 * K) >> 4) * ph_step;
       ((float2 *)a.acc_cur)[s0 + w_mine] = cmul(sA[(phb & 0x7fffu) >> 8], tot);
     }
     stage = stage + 1 == stages ? 0 : stage + 1;
