@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
     for (int i = 0; i + 1 < S; ++i) ring[i] = ld_stream(xc + 32 * i);
     ring[S - 1] = make_float2(0.f, 0.f);
     if (last_ok) ring[S - 1] = ld_stream(xc + 32 * (S - 1));
+    float2 carry = make_float2(0.f, 0.f);
     for (;;) {
       uint32_t nid = id + 1;
       bool more = nid < end, switched = false;
@@ -224,8 +225,12 @@ __global__ void __launch_bounds__(kFoldThreads, S <= 8 ? 4 : (S <= 13 ? 3 : 2)) 
         if (P & 4) { tot.x += R[u].x; tot.y += R[u].y; }
         else cfma(tot, sH[(r0 + u * inc32) & 255u], R[u]);
       }
+      // the tails this window owes to the next one stay in registers while the warp walks consecutive windows
+      // (15 of 16): one staged row per window instead of two
+      tot.x += carry.x; tot.y += carry.y;
       stage.push(tot, id, lane, acc_out);
-      if (L1 > 0 && !(P & 1)) stage.push(sent, id + 1, lane, acc_out);
+      carry = sent;
+      if ((!more || switched) && L1 > 0 && !(P & 1)) { stage.push(carry, id + 1, lane, acc_out); carry = make_float2(0.f, 0.f); }
       if (!more) break;
       if (switched) {
         end = min(nid + kWorkChunk, a.fast_hi + 1);
