@@ -30,6 +30,12 @@ __device__ __forceinline__ void cfma(float2 &acc, float2 w, float2 x) {
   acc.x = fmaf(w.x, x.x, acc.x); acc.x = fmaf(-w.y, x.y, acc.x);
   acc.y = fmaf(w.x, x.y, acc.y); acc.y = fmaf(w.y, x.x, acc.y);
 }
+// The same complex multiply-add as two packed FP32 FMAs (sm_100 FFMA2: the half swap and the sign of one half are operand
+// modifiers): half the issue slots at the same FMA-pipe time -- for kernels that are issue-bound with many resident warps.
+__device__ __forceinline__ void cfma_packed(float2 &acc, float2 w, float2 x) {
+  acc = __ffma2_rn(x, make_float2(w.x, w.x), acc);
+  acc = __ffma2_rn(make_float2(-x.y, x.x), make_float2(w.y, w.y), acc);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
