@@ -87,3 +87,28 @@ def test_per_window_kernel_fused_chain():
     oas = [ofm.process(b, inplace=True) for b in obs]
     assert rel_rms(yb.astype(np.float64).view(np.complex128), np.concatenate(obs).astype(np.float64).view(np.complex128)) < FLOAT_TOL
     assert rel_rms(ya, np.concatenate(oas)) < FLOAT_TOL
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_per_window_kernel_random_configs(seed):
+    """Seeded random geometries (ss 2..256, 1..ss+1 taps, any shift), random call cuts, device input at odd sample
+    offsets (8-byte aligned pointers: the bulk-copy path's unaligned first / last sample)."""
+    import torch
+    rng = np.random.default_rng(1000 + seed)
+    ss = int(rng.integers(2, 257))
+    order = int(rng.integers(1, min(ss + 1, 200) + 1))
+    Fs = 20e6
+    Fc = float(rng.choice([0.0, 1.25e6, -2.5e6, rng.uniform(-9e6, 9e6)]))
+    n = 150000 + int(rng.integers(0, 4096))
+    x = synth.iq_f32(n + 1, Fs, [(0.5, Fc + 3e3, 0.3), (0.3, -4e6, 1.0)], 0.02, 100 + seed)
+    xd = torch.from_numpy(x).cuda()[1:]                 # odd element offset
+    x = x[1:]
+    g, o = _pair(order, ss, Fc, n)
+    cuts = np.unique(np.concatenate([[0, n], rng.integers(1, n, 4)]))
+    ys, os_ = [], []
+    for s_, e_ in zip(cuts[:-1], cuts[1:]):
+        ys.append(g.process(xd[s_:e_]).cpu().numpy()); os_.append(o.process(x[s_:e_]))
+        assert ys[-1].shape == os_[-1].shape
+    y, ob = np.concatenate(ys), np.concatenate(os_)
+    e = rel_rms(y.astype(np.float64).view(np.complex128), ob.astype(np.float64).view(np.complex128))
+    assert e < FLOAT_TOL, (e, ss, order, Fc)
