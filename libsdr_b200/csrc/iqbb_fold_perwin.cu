@@ -313,6 +313,12 @@ __global__ void __launch_bounds__(1024, 1) iqbb_fold_f32_perwin16_kernel(const I
           case 8: acc[k] = mac_window<8>(pv, px, n_steps, last_ok); break;
           case 9: acc[k] = mac_window<9>(pv, px, n_steps, last_ok); break;
           case 10: acc[k] = mac_window<10>(pv, px, n_steps, last_ok); break;
+          case 11: acc[k] = mac_window<11>(pv, px, n_steps, last_ok); break;
+          case 12: acc[k] = mac_window<12>(pv, px, n_steps, last_ok); break;
+          case 13: acc[k] = mac_window<13>(pv, px, n_steps, last_ok); break;
+          case 14: acc[k] = mac_window<14>(pv, px, n_steps, last_ok); break;
+          case 15: acc[k] = mac_window<15>(pv, px, n_steps, last_ok); break;
+          case 16: acc[k] = mac_window<16>(pv, px, n_steps, last_ok); break;
           default: acc[k] = mac_window<0>(pv, px, n_steps, last_ok); break;
         }
       }
@@ -408,7 +414,15 @@ bool fold_perwin_eligible(IqbbFoldArgs &a) {
   const int64_t hi = ((int64_t)a.n - win_off) / ss - 1;        // (hi + 1) ss + win_off <= n
   if (hi < lo) return false;
   a.d_lo = (uint32_t)lo; a.d_hi = (uint32_t)hi;
-  return ((size_t)a.v_rows * a.v_pitch + 1 + 2 * tile_elems(a, a.ss <= pw1_max() ? 0 : 1, nullptr)) * sizeof(float2) <= kPwMaxSmem;
+  if (((size_t)a.v_rows * a.v_pitch + 1 + 2 * tile_elems(a, a.ss <= pw1_max() ? 0 : 1, nullptr)) * sizeof(float2) > kPwMaxSmem) return false;
+  if (a.ss > pw1_max() && a.taps_len <= 129) {
+    // a table that leaves room for fewer than four thread groups: the window-pipelined kernel is faster (measured, 2 groups:
+    // ss 96 / 97 taps 2.7 vs 3.5 TB/s, 100 / 101 2.8 vs 3.3, 128 / 20 4.2 vs 4.3; 4 groups: 96 / 64 5.2 vs 3.5)
+    int k = 1, groups = 1;
+    shape16(a, ((size_t)a.v_rows * a.v_pitch + 1) & ~(size_t)1, &k, &groups);
+    if (groups < 4) return false;
+  }
+  return true;
 }
 
 int launch_fold_perwin(const IqbbFoldArgs &a_in, cudaStream_t st) {

@@ -27,7 +27,13 @@ def _pair(order, ss, Fc, bs):
 
 
 def _table_fits(order, ss):
-    return ss * ((ss + order - 1) | 1) * 8 <= 160 * 1024      # <= ss distinct rows (api.cu upload_fold_tables)
+    """The per-window kernel is used when the V table (<= ss rows, api.cu upload_fold_tables) leaves room for two tile
+    buffers for each of four 256-thread groups (half-warp mapping, ss >= 24), resp. fits at all (thread per window)."""
+    table = ss * ((ss + order - 1) | 1) * 8
+    if ss <= 23:
+        return table <= 160 * 1024
+    tile = (order - 1 + 16 * ss + 4) * 8
+    return table + 8 * tile <= 220 * 1024
 
 
 @pytest.mark.parametrize("ss,order", [(2, 2), (2, 3), (3, 4), (7, 8), (8, 9), (15, 15), (16, 15), (16, 17), (17, 5), (24, 25),
