@@ -14,16 +14,16 @@
 // Mapping.  Tiles of consecutive windows (+ L-1 halo, read once from HBM) go through two shared-memory buffers per
 // thread group, so the copy of the next tile is in flight while one is summed.  The shared-memory pipe is what bounds
 // these kernels (16 bytes of LDS per multiply-add), so both mappings are built around conflict-free accesses:
-//  * ss >= 24 (iqbb_fold_f32_perwin16_kernel<K>, K = 1, 2, 4): a half warp per window, lanes over j.  x and V are read
+//  * ss >= 23 (iqbb_fold_f32_perwin16_kernel<K>, K = 1, 2, 4): a half warp per window, lanes over j.  x and V are read
 //    as 16 consecutive float2 (no conflicts, no padding, halo and window contiguous), every half warp sums K windows one
 //    after the other and the 16 x K partial sums are combined by a transposed reduction (K/2 + K/4 + ... + 4 shuffles
 //    per component instead of 4 K).  The V table exists once per CTA and can take most of the shared memory, so there
 //    is ONE CTA per SM, split into up to four groups of 256 threads that run independent tile pipelines (own buffers,
 //    own mbarriers, own named barrier) -- several "CTAs" sharing one table.  Tiles are staged by 1-D bulk copies
 //    (cp.async.bulk, SASS UBLKCP): no LSU issue slots, no registers.
-//  * ss <= 23 (iqbb_fold_f32_perwin1_kernel): a thread per window (a reduction per window would cost more than the
+//  * ss <= 22 (iqbb_fold_f32_perwin1_kernel): a thread per window (a reduction per window would cost more than the
 //    window); windows are laid out with an odd pitch ss + delta so that the 16 lanes of a half warp hit 16 different
-//    banks, and for ss <= 16 the rows of V land in different banks as well (measured crossover with the half-warp mapping: ss = 24); tiles are staged with 8-byte cp.async.
+//    banks, and for ss <= 16 the rows of V land in different banks as well (measured crossover with the half-warp mapping: ss = 23); tiles are staged with 8-byte cp.async.
 // A window whose halo is inside the call is summed and STORED by its thread group alone (nothing else contributes to
 // its slot); the first and last windows of a call -- cut by the call boundary -- take the per-sample path of
 // fold_chunk_general(), restricted to the (sample, window) pairs the whole windows do not cover.
@@ -127,7 +127,7 @@ __device__ __forceinline__ void perwin_edges(const IqbbFoldArgs &a, const Perwin
   }
 }
 
-// ---- ss <= 23: a thread per window -----------------------------------------------------------------------------
+// ---- ss <= 22: a thread per window -----------------------------------------------------------------------------
 constexpr int kPw1Threads = 256;
 
 __global__ void __launch_bounds__(kPw1Threads, 4) iqbb_fold_f32_perwin1_kernel(const IqbbFoldArgs a, const PerwinGeom geo) {
@@ -212,7 +212,7 @@ __device__ __forceinline__ float2 mac_window(const float2 *__restrict__ pv, cons
   return make_float2(b0.x + b1.x, b0.y + b1.y);
 }
 
-// ---- ss >= 24: a half warp per window ----------------------------------------------------------------------------
+// ---- ss >= 23: a half warp per window ----------------------------------------------------------------------------
 // The V table exists once per CTA and can take most of the shared memory, so there is ONE CTA per SM; to keep the SM
 // busy across tile hand-overs the CTA is split into groups of 256 threads that run independent tile pipelines (own ring
 // of buffers, own mbarriers, own named barrier) -- several "CTAs" sharing one table.
@@ -361,7 +361,7 @@ int launch_perwin16(int groups, const IqbbFoldArgs &a, const PerwinGeom &geo, si
   return perwin_launch(iqbb_fold_f32_perwin16_kernel<K>, groups * kPwGroup, a, geo, want > 0 ? want : 1, smem, st, resident_dev, smem_for, smem_max);
 }
 
-static uint32_t pw1_max() { static const int v = env_int("SDRG_FOLD_PERWIN1_MAX", 23); return (uint32_t)v; }   // ss <= this: a thread per window; above: a half warp per window
+static uint32_t pw1_max() { static const int v = env_int("SDRG_FOLD_PERWIN1_MAX", 22); return (uint32_t)v; }   // ss <= this: a thread per window; above: a half warp per window
 
 constexpr size_t kPwMaxSmem = 220 * 1024;
 

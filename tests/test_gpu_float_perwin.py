@@ -28,9 +28,9 @@ def _pair(order, ss, Fc, bs):
 
 def _table_fits(order, ss):
     """The per-window kernel is used when the V table (<= ss rows, api.cu upload_fold_tables) leaves room for two tile
-    buffers for each of four 256-thread groups (half-warp mapping, ss >= 24), resp. fits at all (thread per window)."""
+    buffers for each of four 256-thread groups (half-warp mapping, ss >= 23), resp. fits at all (thread per window)."""
     table = ss * ((ss + order - 1) | 1) * 8
-    if ss <= 23:
+    if ss <= 22:
         return table <= 160 * 1024
     tile = (order - 1 + 16 * ss + 4) * 8
     return table + 8 * tile <= 220 * 1024
