@@ -1,4 +1,5 @@
-// fft8k_kernels.cu -- the 8192 / 4096-point transforms and the block-4096 FFT convolution (BASELINE config 3),
+// fft8k_kernels.cu -- the 8192 / 4096-point transforms (and, in conv8k_kernels.cu on the same stages, fft8k_stages.cuh,
+// the block-4096 FFT convolution of BASELINE config 3),
 // restructured around three facts measured on the radix-16 Stockham kernels they replace
 // (profiles/r01_final_fft_filter_kernel_summary.md: 64-register cap with spills, address/twiddle arithmetic on
 // the ALU pipe costing more issue slots than the butterflies, 3 + 3 shared-memory round trips):
@@ -27,111 +28,10 @@
 //   stage 3: DFT16 over c.  Position 256 qa + 16 qb + qc then holds U[qa + 16 qb + 256 qc].
 // Reference interfaces replaced: FFTPlan<float> (src/fftplan_fftw3.hh:79-142, FFTW3 underneath) and
 // FilterSink/FilterSource (src/filternode.hh:81-88,164-181).
-#include "fft_kernels.cuh"
-#include "fft_device.cuh"
-
-#include <atomic>
-#include <cmath>
-#include <vector>
+#include "fft8k_stages.cuh"
 
 namespace sdrg {
 namespace {
-
-constexpr int kT = 256;                       // threads per CTA
-constexpr int kHalf = 4096;
-// shared-memory position of element i of a half: two pads per 16 and two more per 256, so that lanes striding
-// by 1 (stages 1, 2: 64-bit accesses) or by 256 (stage 3: 128-bit accesses of 16 consecutive elements, whose
-// first position 290 qa + 18 qb is even, i.e. 16-byte aligned) all fall on distinct banks
-__device__ __forceinline__ int pos(int i) { return i + 2 * (i >> 4) + 2 * (i >> 8); }
-// the same written per digit, i = 256 A + 16 B + C: every access below is then [thread base + immediate]
-__host__ __device__ constexpr int pos3(int A, int B, int C) { return 290 * A + 18 * B + C; }
-constexpr int kHalfPad = kHalf + 2 * (kHalf / 16) + 2 * (kHalf / 256) + 8;
-
-// table layout (float2 entries, forward sign exp(-2 pi i k / n))
-constexpr int kT1 = 0;                        // [q][u]  w_4096^(q u), q < 16, u < 256
-constexpr int kT2 = kT1 + 16 * 256;           // [q][c]  w_256^(q c),  q < 16, c < 16
-constexpr int kT8 = kT2 + 16 * 16;            // [u]     w_8192^u,     u < 256
-constexpr int kTabLen = kT8 + 256;
-constexpr size_t kSmemBytes = (size_t)(2 * kHalfPad + kTabLen) * sizeof(float2);
-
-__device__ __forceinline__ void load_tables(float2 *tab, const float2 *__restrict__ g) {
-  for (int i = threadIdx.x; i < kTabLen; i += kT) tab[i] = g[i];
-}
-
-// w_8192^(256 a + t) = w_32^a . w_8192^t; the 16 values of w_32^a are immediates
-__device__ __forceinline__ float2 root8k(const float2 wt, const int a) {
-  constexpr float c32[16] = {1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f,
-                             3.826834324e-01f, 1.950903220e-01f, 0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f,
-                             -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
-  constexpr float s32[16] = {0.000000000e+00f, 1.950903220e-01f, 3.826834324e-01f, 5.555702330e-01f, 7.071067812e-01f, 8.314696123e-01f,
-                             9.238795325e-01f, 9.807852804e-01f, 1.0f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f,
-                             7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f};
-  if (a == 0) return wt;
-  if (a == 8) return make_float2(wt.y, -wt.x);
-  // wt * (c - i s)
-  return make_float2(wt.x * c32[a] + wt.y * s32[a], wt.y * c32[a] - wt.x * s32[a]);
-}
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// ---- the decimation-in-frequency pass (forward; INV conjugates every root => unnormalised backward DFT) ----
-// Both halves go through a stage together: twice the independent work per thread, and every table twiddle is
-// loaded once for the two butterflies that need it.
-// stage 1: e[a] = u0[256 a + t], o[a] = u1[256 a + t] on entry (thread t = 16 b + c)
-// The CTA barrier that frees the buffers (everybody has finished READING the previous item's last stage) sits between
-// the butterflies and the stores, so the global-load latency and the first DFTs of an item overlap the tail of the
-// previous one.
-template <bool INV>
-__device__ __forceinline__ void dif_stage1(float2 *e, float2 *o, float2 *H0, const float2 *tab, const int t) {
-  const int pt = pos3(0, t >> 4, t & 15);
-  dft16<INV>(e);
-  dft16<INV>(o);
-  __syncthreads();
-  H0[pt] = e[0];
-  H0[pt + kHalfPad] = o[0];
-#pragma unroll
-  for (int q = 1; q < 16; ++q) {
-    const float2 w = tab[kT1 + 256 * q + t];
-    H0[pt + pos3(q, 0, 0)] = cmulw<INV>(e[q], w);
-    H0[pt + pos3(q, 0, 0) + kHalfPad] = cmulw<INV>(o[q], w);
-  }
-}
-// stage 2: thread t = 16 qa + c works on positions 256 qa + 16 b + c of both halves
-template <bool INV>
-__device__ __forceinline__ void dif_stage2(float2 *H0, const float2 *tab, const int t) {
-  const int c = t & 15;
-  float2 *B = H0 + pos3(t >> 4, 0, c);
-  float2 e[16], o[16];
-#pragma unroll
-  for (int b = 0; b < 16; ++b) { e[b] = B[pos3(0, b, 0)]; o[b] = B[pos3(0, b, 0) + kHalfPad]; }
-  dft16<INV>(e);
-  dft16<INV>(o);
-  B[0] = e[0];
-  B[kHalfPad] = o[0];
-#pragma unroll
-  for (int q = 1; q < 16; ++q) {
-    const float2 w = tab[kT2 + 16 * q + c];
-    B[pos3(0, q, 0)] = cmulw<INV>(e[q], w);
-    B[pos3(0, q, 0) + kHalfPad] = cmulw<INV>(o[q], w);
-  }
-}
-// stage 3: thread t = qa + 16 qb reads the 16 consecutive positions of 256 qa + 16 qb + c (128-bit loads);
-// on return v[qc] = U[t + 256 qc]
-__device__ __forceinline__ int stage3_pos(const int t) { return pos3(t & 15, t >> 4, 0); }
-// The convolution does not care in which order the bins come out, so its stage 3 uses thread t = 16 qa + qb instead:
-// the 16 positions it reads were all written (stage 2, threads 16 qa + c) by lanes of the SAME warp, and the inverse
-// mirror holds too -- two of the five CTA barriers per block become __syncwarp().  Bins held: qa + 16 qb + 256 qc.
-__device__ __forceinline__ int stage3_pos_conv(const int t) { return pos3(t >> 4, t & 15, 0); }
-__device__ __forceinline__ void load16(float2 *v, const float2 *H, const int p0) {
-  const float4 *h4 = (const float4 *)(H + p0);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { const float4 q = h4[k]; v[2 * k] = make_float2(q.x, q.y); v[2 * k + 1] = make_float2(q.z, q.w); }
-}
-__device__ __forceinline__ void store16(const float2 *v, float2 *H, const int p0) {
-  float4 *h4 = (float4 *)(H + p0);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) h4[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
-}
 
 // ---- FFTPlan<float>: batched 8192-point (SPLIT) or 4096-point (two transforms per iteration) DFT ----------
 template <bool INV, bool SPLIT>
@@ -188,146 +88,8 @@ __global__ void __launch_bounds__(kT, 2) fft8k_kernel(const float2 *__restrict__
   }
 }
 
-// ---- block-4096 overlap-save convolution, fused ------------------------------------------------------------
-// y[N + j] = IDFT_8192(DFT_8192([prev | cur]) K)[N + j] / 8192 = v0[j] - conj(w_8192^j) v1[j], v_h the 4096-point
-// backward DFTs of the even / odd bins.  K arrives permuted and pre-scaled: kp[(h 16 + qc) 256 + t] = K[2 m + h] / 8192,
-// m = (t >> 4) + 16 (t & 15) + 256 qc the bin thread t holds after stage 3.
-// BANK = false: one filter; the last forward stage, the spectrum multiply and the first inverse stage stay in registers.
-// BANK = true: F filters on one FilterSink (src/filternode.hh:262-270).  The forward transform runs once per block; its
-// spectrum (digit-reversed, 64 KB) goes to a CTA-private scratch line in global memory -- written and read back by the
-// SAME thread, so no barrier is involved and, with at most 2 x 148 CTAs, the scratch (19 MB) never leaves L2 -- and
-// every filter then runs the inverse half.
-template <bool BANK>
-__global__ void __launch_bounds__(kT, 2) conv8k_kernel(const FilterArgs a, const int n_blocks) {
-  extern __shared__ __align__(16) unsigned char fft8k_smem[];
-  float2 *H0 = (float2 *)fft8k_smem, *H1 = H0 + kHalfPad, *tab = H1 + kHalfPad;
-  const int t = threadIdx.x;
-  load_tables(tab, (const float2 *)a.tab8k);
-  __syncthreads();
-  const float2 *x = (const float2 *)a.x;
-  float2 *scratch = BANK ? (float2 *)a.spec + (size_t)blockIdx.x * 8192 + t : nullptr;
-  const int n_filters = BANK ? a.n_filters : 1;
-  for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-    const float2 *prev = blk == 0 ? (const float2 *)a.hist_in : x + (size_t)(blk - 1) * kHalf;
-    const float2 *cur = x + (size_t)blk * kHalf;
-    {   // load, radix-2 DIF step, stage 1 of both halves
-      float2 e[16], o[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { e[q] = prev[256 * q + t]; o[q] = cur[256 * q + t]; }
-      if (blk + (int)gridDim.x < n_blocks) {   // this CTA's next block pair: 64 KB into L2 while this one is computed
-        const char *nx = (const char *)(cur + ((size_t)gridDim.x - 1) * kHalf);
-        prefetch_l2(nx + 128 * t); prefetch_l2(nx + 128 * (t + 256));
-      }
-      if (blk == n_blocks - 1) {
-        float2 *ho = (float2 *)a.hist_out;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) ho[256 * q + t] = o[q];
-      }
-      const float2 wt = tab[kT8 + t];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float2 p = e[q], c = o[q];
-        e[q] = caddf(p, c);
-        o[q] = cmulf(csubf(p, c), root8k(wt, q));
-      }
-      dif_stage1<false>(e, o, H0, tab, t);
-    }
-    __syncthreads();
-    dif_stage2<false>(H0, tab, t);
-    __syncwarp();                // stage 3 reads what lanes of this warp wrote (see stage3_pos_conv)
-    const int qb = t & 15, p0 = stage3_pos_conv(t);
-    if (BANK) {      // forward stage 3 -> the CTA's scratch line
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float2 v[16];
-        load16(v, h ? H1 : H0, p0);
-        dft16<false>(v);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) scratch[(h * 16 + q) * 256] = v[q];
-      }
-    }
-    for (int f = 0; f < n_filters; ++f) {
-      const float2 *kp = (const float2 *)a.kperm + (size_t)f * 8192 + t;
-      // (stage 3,) spectrum multiply, first inverse stage (DFT16 over qc, twiddle conj w_256^(c qb)); the filter
-      // spectrum is requested first so that its latency hides behind the shared-memory reads and the DFT
-      {
-        float2 v0[16], v1[16];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float2 *v = h ? v1 : v0;
-          float2 k[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) k[q] = __ldg(kp + (h * 16 + q) * 256);
-          if (BANK) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = scratch[(h * 16 + q) * 256];
-          } else {
-            load16(v, h ? H1 : H0, p0);
-            dft16<false>(v);
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = cmulf(v[q], k[q]);
-#pragma unroll
-          for (int q = 8; q < 16; ++q) v[q] = cmulf(v[q], __ldg(kp + (h * 16 + q) * 256));
-          dft16<true>(v);
-        }
-#pragma unroll
-        for (int c = 1; c < 16; ++c) {
-          const float2 w = tab[kT2 + 16 * c + qb];
-          v0[c] = cmulw<true>(v0[c], w);
-          v1[c] = cmulw<true>(v1[c], w);
-        }
-        store16(v0, H0, p0);
-        store16(v1, H1, p0);
-      }
-      __syncwarp();
-      {   // second inverse stage: thread t = 16 qa + c, DFT16 over qb, twiddle conj w_4096^(qa (16 b + c))
-        const int qa = t >> 4, c = t & 15;
-        float2 *B = H0 + pos3(qa, 0, c);
-        const float2 *T = tab + kT1 + 256 * qa + c;
-        float2 e[16], o[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) { e[q] = B[pos3(0, q, 0)]; o[q] = B[pos3(0, q, 0) + kHalfPad]; }
-        dft16<true>(e);
-        dft16<true>(o);
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {         // (w_4096^(qa (16 b + c)) is 1 only for qa = 0: no row to skip here)
-          const float2 w = T[16 * b];
-          B[pos3(0, b, 0)] = cmulw<true>(e[b], w);
-          B[pos3(0, b, 0) + kHalfPad] = cmulw<true>(o[b], w);
-        }
-      }
-      __syncthreads();
-      {   // third inverse stage of both halves (thread t = 16 b + c, DFT16 over qa) and the overlap-save combine
-        const float2 *B = H0 + pos3(0, t >> 4, t & 15);
-        float2 z[16], v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) z[q] = B[pos3(q, 0, 0) + kHalfPad];
-        dft16<true>(z);
-        const float2 wt = tab[kT8 + t];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) { z[q] = cmulw<true>(z[q], root8k(wt, q)); v[q] = B[pos3(q, 0, 0)]; }
-        dft16<true>(v);
-        float2 *o = (float2 *)a.out + (size_t)f * a.out_stride + (size_t)blk * kHalf + t;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) o[256 * q] = csubf(v[q], z[q]);
-      }
-      if (BANK && f + 1 < n_filters) __syncthreads();   // the next filter's first-stage stores; the next BLOCK waits inside dif_stage1
-    }
-  }
-}
-
-int resident_ctas(const void *fn, int dev, std::atomic<int> *cache) {
-  if (!cache[dev]) {
-    int sms = 0, per_sm = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kT, kSmemBytes);
-    cache[dev] = sms * (per_sm > 0 ? per_sm : 1);
-  }
-  return cache[dev];
-}
-
 }  // namespace
+
 
 // host: the shared tables, double precision rounded once
 void fft8k_tables(std::vector<float> &tab) {
@@ -378,37 +140,6 @@ int launch_fft8k(const void *in, void *out, int n, int inverse, size_t batch, co
     else fft8k_kernel<false, false><<<grid, kT, kSmemBytes, st>>>(i2, o2, (int)batch, t2);
   }
   SDRG_CHECK_LAUNCH("fft8k_kernel");
-  return SDRG_OK;
-}
-
-int conv8k_grid(size_t n_blocks) {      // CTAs launch_conv8k will use (the bank's scratch is 64 KB per CTA)
-  const int dev = current_device();
-  static std::atomic<int> attr[kMaxDevices];
-  if (!attr[dev]) {
-    if (cudaFuncSetAttribute(conv8k_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(conv8k_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) {
-      cudaGetLastError();
-      return 0;
-    }
-    attr[dev] = 1;
-  }
-  static std::atomic<int> res[kMaxDevices];
-  const int resident = resident_ctas((const void *)conv8k_kernel<true>, dev, res);
-  return (int)(n_blocks < (size_t)resident ? n_blocks : (size_t)resident);
-}
-
-int launch_conv8k(const FilterArgs &a, size_t n_blocks, cudaStream_t st) {
-  if (n_blocks == 0) return SDRG_OK;
-  if (n_blocks > 0x7fffffffull) return set_error(SDRG_ERR_ARG, "FilterNode: too many blocks in one call");
-  const int grid = conv8k_grid(n_blocks);
-  if (grid <= 0) return set_error(SDRG_ERR_CUDA, "FilterNode: cannot configure the block-4096 kernel");
-  if (a.n_filters > 1) {
-    if (!a.spec) return set_error(SDRG_ERR_RUNTIME, "FilterNode: the filter bank needs its spectrum scratch");
-    conv8k_kernel<true><<<grid, kT, kSmemBytes, st>>>(a, (int)n_blocks);
-  } else {
-    conv8k_kernel<false><<<grid, kT, kSmemBytes, st>>>(a, (int)n_blocks);
-  }
-  SDRG_CHECK_LAUNCH("conv8k_kernel");
   return SDRG_OK;
 }
 

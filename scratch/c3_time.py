@@ -6,14 +6,18 @@ c = synth.C3
 x = torch.from_numpy(synth.c2_input(1 << 20)).cuda().repeat(16, 1).view(torch.complex64).reshape(-1)
 
 
-def timed(fn, reps=9):
+def timed(fn, reps=7, inner=20):
+    """median over `reps` of `inner` back-to-back calls between two events (launch gaps excluded, like bench.py)"""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / inner)
     ts.sort()
     return ts[len(ts) // 2]
 
